@@ -1,0 +1,328 @@
+"""bench.py -- headline metric of BASELINE.json on B200: whisper-large-v3 tokens/sec (and RTF) on 30 s chunks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic 30 s chunks on every rank:
+PCM -> log-mel -> 32-layer encoder -> cross K/V -> `new_tokens` greedy decoder steps -> token ids.
+  value : whole-job tokens/s with the PCM already resident in HBM (device-timed, max over ranks)
+  e2e   : the same through the public API (thestage-style ASRPipeline call) with HOST buffers: pinned H2D of the PCM
+          and D2H of the token ids inside the timed region
+Workload = BASELINE.json configs[1]: whisper-large-v3 dims, random weights (no checkpoint offline), one synthetic
+30 s chunk per GPU, greedy, EOS suppressed so exactly `new_tokens` tokens are produced.
+Independent chunks shard across ranks with no data-path collective (weak scaling); the only collective is the weight
+broadcast at init.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
+
+NEW_TOKENS = 128
+PRESET = os.environ.get("BW_BENCH_PRESET", "large-v3")
+CHUNK_S = 30
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def decode_bytes_per_step(dims, S: int, A: int, t_mean: float) -> float:
+    """Algorithmic HBM bytes of one decoder step: weights + A * cross-KV + A * self-KV(t)."""
+    d, L, V, ffn = dims.d_model, dims.dec_layers, dims.vocab, dims.ffn
+    w = 2.0 * (L * (8 * d * d + 2 * d * ffn) + V * d)
+    xkv = 2.0 * L * 2 * S * d
+    skv = 2.0 * L * 2 * t_mean * d
+    return w + A * xkv + A * skv
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU path (HF transformers driven by the restated reference glue in
+    oracle/hf_ref.py -- the reference package itself cannot travel to the GPU box) on the host cores."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    new_tokens = int(os.environ.get("BW_REF_TOKENS", "16"))
+    model = S.make_hf_model(PRESET, seed=0)
+    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True)
+    fe, tok = S.make_feature_extractor(CHUNK_S), S.make_tokenizer()
+    pipe = hf_ref.make_ref_pipeline(model, fe, tok, chunk_length_s=CHUNK_S, device="cpu")
+    audio = S.synth_audio(CHUNK_S, seed=1000)
+    gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": new_tokens}
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pipe(audio.copy(), generate_kwargs=dict(gk))
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = new_tokens / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whisper-{PRESET} dims, 1 x {CHUNK_S}s synthetic chunk, greedy, {new_tokens} new tokens (bounded sample)",
+                   "new_tokens": new_tokens, "rtf": (ms / 1e3) / CHUNK_S},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port",
+                         "sample": f"1 chunk x {new_tokens} tokens x {args.steps} steps, HF transformers fp32 via oracle/hf_ref.py"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.engine import DecodeOptions, ModelDims, WhisperEngine, interpolate_positions, pack_weights
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- weights: rank 0 builds the random checkpoint, one NCCL broadcast at init, nothing per step
+    cfg = S.make_hf_config(PRESET)
+    dims = ModelDims.from_hf_config(cfg)
+    t0 = time.time()
+    if rank == 0:
+        model = S.make_hf_model(PRESET, seed=0)
+        sd = model.state_dict()
+        weights = pack_weights(sd, dims, sd["model.encoder.embed_positions.weight"].float(), dev)
+        meta = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in weights.items()]
+        del model, sd
+    else:
+        weights, meta = None, None
+    if world > 1:
+        box = [meta]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        if rank != 0:
+            weights = {k: torch.empty(shape, dtype=getattr(torch, dt), device=dev) for k, shape, dt in meta}
+        for k, _, _ in meta:
+            dist.broadcast(weights[k], src=0)
+        torch.cuda.synchronize()
+    t_weights = time.time() - t0
+
+    A = 1  # chunks per GPU per step (configs[1])
+    gcfg = S.make_generation_config(PRESET, eos_suppressed=True)
+    eng = WhisperEngine({}, dims, chunk_length_s=CHUNK_S, device=str(dev), max_audios=A, max_beams=1, weights=weights)
+    opts = DecodeOptions(eos_token=S.EOS, pad_token=S.EOS, suppress_tokens=list(gcfg.suppress_tokens),
+                         begin_suppress_tokens=list(gcfg.begin_suppress_tokens))
+    prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]] * A, dtype=np.int32)
+    pcm = np.stack([S.synth_audio(CHUNK_S, seed=1000 + rank * A + i) for i in range(A)])
+    pcm_dev = torch.from_numpy(pcm).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        eng.logmel_device(pcm_dev, A)
+        eng.encode(A)
+        eng.decode_begin(prompt, A, 1, opts)
+        eng.decode_run(prompt.shape[1] - 1 + NEW_TOKENS)
+
+    def step_e2e():
+        eng.logmel(pcm)  # pinned staging + H2D inside
+        eng.encode(A)
+        eng.decode_begin(prompt, A, 1, opts)
+        eng.decode_run(prompt.shape[1] - 1 + NEW_TOKENS)
+        toks, fin, pos = eng.decode_read()  # D2H of the ids
+        return toks
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # ---- roofline of the dominant kernel family: the decoder step (HBM stream), timed alone on its stream
+    def decode_only():
+        eng.decode_begin(prompt, A, 1, opts)
+        eng.decode_run(prompt.shape[1] - 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.decode_run(NEW_TOKENS)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / NEW_TOKENS
+
+    step_ms = float(np.median([decode_only() for _ in range(5)]))
+    clocks = sampler.stop() if rank == 0 else None
+    toks = step_e2e()
+    assert toks.shape[0] == A and (toks[:, 4:4 + NEW_TOKENS] >= 0).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, how = _peaks()
+    bytes_step = decode_bytes_per_step(dims, eng.S, A, 4 + NEW_TOKENS / 2)
+    achieved = bytes_step / (step_ms * 1e-3) / 1e9
+    tokens = A * NEW_TOKENS * world
+    n_dec_kernels = 1 + dims.dec_layers * 8 + 2
+    n_enc_kernels = 2 + 2 + dims.enc_layers * 8 + 1 + 2 * dims.dec_layers
+    line = {
+        "metric": "tokens_per_sec", "value": tokens / (ms_res / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"whisper-{PRESET} dims (random weights), {A} x {CHUNK_S}s synthetic chunk per GPU, greedy, "
+                               f"{NEW_TOKENS} new tokens (EOS suppressed)", "chunks_per_gpu": A, "new_tokens": NEW_TOKENS,
+                   "parallelism": f"dp{world} (independent chunks, weights broadcast once in {t_weights:.1f}s)",
+                   "l2": "256 MB flush write between timed iterations", "rtf": (ms_res / 1e3) / (CHUNK_S * A),
+                   "rtfx": (CHUNK_S * A) / (ms_res / 1e3), "decode_only_tokens_per_sec": A * 1e3 / step_ms,
+                   "published_reference_headline": "220 tok/s on L40s (README.md:19), other hardware"},
+        "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(pcm.nbytes + prompt.nbytes),
+                "d2h_bytes_per_step": int(A * dims.max_target_positions * 4 + A * 4 + 4), "ms_per_step": ms_e2e,
+                "rtf": (ms_e2e / 1e3) / (CHUNK_S * A)},
+        "gpu_launches": args.steps * (n_enc_kernels + (3 + NEW_TOKENS) * n_dec_kernels + 3),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "decoder step (gemv/attention/select family, one CUDA graph)", "achieved": achieved,
+                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": how, "traffic": None,
+                     "bytes_per_step": bytes_step, "ms_per_decoder_step": step_ms},
+    }
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as ex:  # the GPU numbers stand on their own
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "error": repr(ex)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """Bounded CPU sample of the same workload through the oracle (kind "port": restated reference glue over the
+    installed transformers), on this box's host cores."""
+    import torch
+
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nt = 8
+    model = S.make_hf_model(PRESET, seed=0)
+    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True)
+    pipe = hf_ref.make_ref_pipeline(model, S.make_feature_extractor(CHUNK_S), S.make_tokenizer(), chunk_length_s=CHUNK_S, device="cpu")
+    audio = S.synth_audio(CHUNK_S, seed=1000)
+    gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": nt}
+    pipe(audio.copy(), generate_kwargs=dict(gk))
+    t0 = time.perf_counter()
+    pipe(audio.copy(), generate_kwargs=dict(gk))
+    dt = time.perf_counter() - t0
+    return {"value": nt / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"1 x {CHUNK_S}s chunk, {nt} greedy tokens, fp32 HF transformers on CPU, 1 warm-up + 1 timed call ({dt:.1f}s)"}
+
+
+if __name__ == "__main__":
+    main()

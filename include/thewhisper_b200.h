@@ -1,0 +1,117 @@
+/* thewhisper_b200 -- C-ABI of the B200-native Whisper hot path (log-mel -> encoder -> decoder -> tokens).
+ *
+ * This is the drop-in boundary below `thestage_speechkit.nvidia.ASRPipeline.__call__`
+ * (reference: /root/reference/thestage_speechkit/nvidia/asr_pipeline.py:30-92).  The reference has no native
+ * code and no FFI: everything numeric is reached through `transformers` (un-vendored), so each entry point cites
+ * the Python call it replaces (TF = transformers 5.5.0 as installed; the reference pins 4.52.3):
+ *
+ *   bw_logmel            TF/models/whisper/feature_extraction_whisper.py:135-164  (_torch_extract_fbank_features)
+ *   bw_encode            TF/models/whisper/modeling_whisper.py:593-647 (WhisperEncoder.forward) + :331-336 (cross K/V)
+ *   bw_decode_begin/run  TF/generation/utils.py:2743-2809 (_sample loop) over modeling_whisper.py:691-796,1081 and
+ *                        the processors TF/generation/logits_process.py:1812-2043
+ *   bw_word_timestamps   TF/models/whisper/generation_whisper.py:241-381 (_extract_token_timestamps, DTW :64-115)
+ *
+ * Conventions: plain C, no torch types.  Every function returns 0 on success and a negative code on error; the
+ * message is available from bw_last_error() (thread-local).  Nothing throws across the boundary.  Device pointers
+ * are caller-owned (the Python host passes torch storage); `stream` is a cudaStream_t cast to void* and all work
+ * is enqueued asynchronously on it.  One engine per GPU / process; an engine is not re-entrant.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef THEWHISPER_B200_H_
+#define THEWHISPER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BW_ABI_VERSION 1
+
+typedef struct bw_engine bw_engine;
+
+typedef struct bw_config {
+  int32_t d_model;      /* 1280 */
+  int32_t n_heads;      /* 20  (head_dim must be 64) */
+  int32_t ffn;          /* 5120 */
+  int32_t enc_layers;   /* 32 */
+  int32_t dec_layers;   /* 32 (4 for turbo) */
+  int32_t n_mels;       /* 128 */
+  int32_t vocab;        /* 51866 */
+  int32_t max_source_positions; /* S: 1500 (30 s), 1000, 750, 500 -- set by chunk_length_s */
+  int32_t max_target_positions; /* 448 */
+  int32_t max_audios;   /* A: audios per encode/decode call */
+  int32_t max_beams;    /* G <= 8 sequences sharing one audio's cross K/V */
+  int32_t n_align_heads;/* alignment heads for word timestamps (0 = off) */
+  int32_t max_align_steps; /* rows of alignment scores kept per audio (<= max_target_positions) */
+} bw_config;
+
+typedef struct bw_decode_opts {
+  int32_t begin_index;        /* prompt length: positions < begin_index are teacher-forced */
+  int32_t eos_token, pad_token;
+  int32_t timestamp_rules;    /* 1 = WhisperTimeStampLogitsProcessor on */
+  int32_t timestamp_begin, no_timestamps_token, max_initial_timestamp_index; /* -1 = none */
+  const int32_t* suppress_tokens; int32_t n_suppress;             /* host arrays */
+  const int32_t* begin_suppress_tokens; int32_t n_begin_suppress;
+  int32_t record_alignment;   /* 1 = keep cross-attention scores of the alignment heads */
+} bw_decode_opts;
+
+const char* bw_last_error(void);
+int bw_abi_version(void);
+int bw_device_count(void);
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+int bw_engine_create(const bw_config* cfg, bw_engine** out);
+void bw_engine_destroy(bw_engine* e);
+/* Bind one weight tensor by name (device pointer, must outlive the engine).  Matrices are bf16 row-major
+ * [out, in] (torch Linear layout), vectors fp32.  Names: see DESIGN.md "weights". */
+int bw_engine_set_tensor(bw_engine* e, const char* name, const void* device_ptr);
+/* slaney mel filter bank [201, n_mels] fp32 on the HOST (TF/audio_utils.py:453-544), copied to the device. */
+int bw_engine_set_mel_filters(bw_engine* e, const float* bank_host);
+/* alignment heads as (layer, head) pairs on the host */
+int bw_engine_set_alignment_heads(bw_engine* e, const int32_t* layer_head_pairs, int32_t n);
+/* checks that every tensor is bound and allocates the workspace + KV caches */
+int bw_engine_finalize(bw_engine* e);
+/* device pointer + size of an internal buffer ("mel_tm", "x_enc", "enc_out", "logits", "tokens", "align", ...) */
+int bw_engine_buffer(bw_engine* e, const char* name, void** device_ptr, size_t* bytes);
+
+/* ---- hot path ------------------------------------------------------------------------------------------------ */
+/* pcm: device fp32 [B, n_samples], n_samples == 320 * max_source_positions (chunk already zero-padded/truncated).
+ * Writes the engine's mel buffer; if mel_f32_out != NULL also the reference layout [B, n_mels, frames] fp32. */
+int bw_logmel(bw_engine* e, const float* pcm, int32_t B, int32_t n_samples, float* mel_f32_out, void* stream);
+/* load externally computed features instead (device fp32 [B, n_mels, frames]) */
+int bw_set_mel(bw_engine* e, const float* mel_f32, int32_t B, void* stream);
+/* conv stem + encoder layers + final LayerNorm + cross-attention K/V projection of every decoder layer */
+int bw_encode(bw_engine* e, int32_t B, void* stream);
+/* start a decode over A audios x G sequences; prompt_host: [A*G, prompt_len] int32 */
+int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt_host, int32_t prompt_len,
+                    const bw_decode_opts* opts, void* stream);
+/* run n decoder steps (one CUDA-graph launch each, no host synchronisation) */
+int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream);
+/* synchronises the stream; tokens_host [A*G, max_target_positions], finished_host [A*G] (either may be NULL) */
+int bw_decode_read(bw_engine* e, int32_t* tokens_host, int32_t* finished_host, int32_t* pos_host, void* stream);
+/* beam search support: reorder sequences (new sequence i continues old sequence parent[i]) by permuting the
+ * per-token block table; overwrite the token just selected.  Host arrays of A*G entries. */
+int bw_decode_reorder(bw_engine* e, const int32_t* parent_host, const int32_t* next_token_host, void* stream);
+/* word timestamps for audio a: n_tokens generated tokens starting at alignment row 0, num_frames valid encoder
+ * frames (<= S); out_host [n_tokens + 1] seconds */
+int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision,
+                       float* out_host, void* stream);
+
+/* ---- single-op entry points (used by the parity tests; same kernels as the engine) --------------------------- */
+/* C[M,N] = epi(A[M,K] W[N,K]^T): impl 0 = tcgen05, 1 = CUDA-core comparator.  out_is_f32 selects the output type. */
+int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,
+               const float* residual, void* out, int32_t out_is_f32, int32_t impl, int32_t force_bn, void* stream);
+/* qkv [B*S, 3D] bf16 -> out [B*S, D] bf16; vt_scratch [B, H, 64, Spad] bf16 (Spad = S rounded up to 8) */
+int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int32_t S, int32_t H, int32_t impl, void* stream);
+int bw_op_layernorm(const float* x, const float* g, const float* b, void* out, int32_t out_is_f32, int32_t rows, int32_t D,
+                    void* stream);
+/* out[M,N] fp32 = epi(LN?(x[M,K]) W[N,K]^T), M <= 8 */
+int bw_op_gemv(const float* x, const float* ln_g, const float* ln_b, const void* W, int32_t M, int32_t N, int32_t K,
+               const float* bias, float alpha, int32_t act, const float* residual, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEWHISPER_B200_H_ */

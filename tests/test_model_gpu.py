@@ -1,0 +1,204 @@
+"""End-to-end parity of the CUDA path (through the C-ABI engine) against the oracle (HF transformers on the CPU,
+oracle/hf_ref.py) and the committed golden fixtures minted from the real reference (oracle/make_golden.py).
+
+Bars (task statement ③): token ids identical under greedy decoding wherever the oracle's own top-1/top-2 margin
+exceeds the measured logit tolerance; log-mel within 2e-4 abs (fp32 FFT vs torch.stft; the reference itself
+claims 1e-5 between its two CPU implementations) and logits within 2% of the logit standard deviation
+(bf16 operands, fp32 accumulation, fp32 residual stream)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLD
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(model, chunk_s, **kw):
+    from thewhisper_b200.engine import ModelDims, WhisperEngine
+
+    return WhisperEngine(model.state_dict(), ModelDims.from_hf_config(model.config), chunk_length_s=chunk_s, **kw)
+
+
+def _opts(model, ts=False, align=False):
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.engine import DecodeOptions
+
+    g = model.generation_config
+    return DecodeOptions(eos_token=S.EOS, pad_token=S.EOS, suppress_tokens=list(g.suppress_tokens),
+                         begin_suppress_tokens=list(g.begin_suppress_tokens), timestamp_rules=ts,
+                         timestamp_begin=S.TIMESTAMP_BEGIN, no_timestamps_token=S.NOTIMESTAMPS,
+                         max_initial_timestamp_index=g.max_initial_timestamp_index if ts else -1, record_alignment=align)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# log-mel
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("secs", [10, 15, 30])
+def test_logmel_golden(cuda, secs):
+    from thewhisper_b200 import synthetic as S
+
+    gold = np.load(os.path.join(GOLD, "logmel.npz"))
+    model = S.make_hf_model("tiny-test")
+    eng = _engine(model, secs, max_audios=2)
+    x = S.two_tone(secs)
+    mel = eng.logmel(np.stack([x, x]), return_f32=True).cpu().numpy()
+    assert mel.shape == (2, 128, secs * 100)
+    assert np.array_equal(mel[0], mel[1])
+    sub = gold[f"two_tone_{secs}s_sub"]
+    err = np.abs(mel[0][:, ::25] - sub).max()
+    assert err < 2e-4, err
+    st = gold[f"two_tone_{secs}s_stats"]
+    assert abs(mel[0].mean() - st[0]) < 1e-5 and abs(mel[0].max() - st[2]) < 1e-4
+
+
+def test_logmel_noise_and_padding(cuda):
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.features import pad_or_trim
+
+    gold = np.load(os.path.join(GOLD, "logmel.npz"))
+    model = S.make_hf_model("tiny-test")
+    eng = _engine(model, 10, max_audios=3)
+    noise = (np.random.RandomState(0).randn(160000) * 0.1).astype(np.float32)
+    short = S.synth_audio(7.3, seed=11)
+    speech = S.synth_audio(10, seed=5)
+    batch = np.stack([noise, pad_or_trim(short, 160000), speech])
+    mel = eng.logmel(batch, return_f32=True).cpu().numpy()
+    assert np.abs(mel[0][:, ::10] - gold["noise_10s_sub"]).max() < 2e-4
+    assert np.abs(mel[1][:, ::10] - gold["speech_7p3s_sub"]).max() < 2e-4
+    fe = S.make_feature_extractor(10)
+    ref = hf_ref.logmel(fe, speech)  # oracle live, full array
+    assert np.abs(mel[2] - ref).max() < 2e-4
+    # the bf16 time-major copy the conv stem consumes
+    tm = eng.buffer("mel_tm", torch.bfloat16, (3, 1002, 128)).float().cpu().numpy()
+    assert np.all(tm[:, 0] == 0) and np.all(tm[:, -1] == 0)
+    assert np.abs(tm[2, 1:-1].T - ref).max() < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# encoder / decoder on the small random checkpoints of the golden files
+# ------------------------------------------------------------------------------------------------------------------
+def _model_case(tag):
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, f"model_{tag}.json")))
+    gold = np.load(os.path.join(GOLD, f"model_{tag}.npz"))
+    model = S.make_hf_model(meta["preset"], seed=meta["seed"], layer_gain=meta.get("layer_gain", 1.0))
+    return meta, gold, model
+
+
+def _oracle_model(model, chunk_s):
+    from oracle import hf_ref
+
+    if chunk_s < 30 and model.config.max_source_positions == 1500:
+        hf_ref.interpolate_positions(model, chunk_s)
+    return model
+
+
+@pytest.mark.parametrize("tag", ["tiny10", "small30"])
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_encoder_parity(cuda, tag, impl, monkeypatch):
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    if impl == "simt":
+        monkeypatch.setenv("BW_GEMM_IMPL", "simt")
+    meta, gold, model = _model_case(tag)
+    chunk = meta["chunk_s"]
+    eng = _engine(model, chunk, max_audios=2)
+    fe = S.make_feature_extractor(chunk)
+    a0, a1 = S.synth_audio(chunk, seed=1000), S.synth_audio(chunk, seed=1001)
+    mels = np.stack([hf_ref.logmel(fe, a0), hf_ref.logmel(fe, a1)])
+    eng.set_mel(torch.from_numpy(mels))
+    eng.encode(2)
+    out = eng.encoder_output(2).cpu().numpy()
+    om = _oracle_model(model, chunk)
+    ref0, ref1 = hf_ref.encoder_out(om, mels[0]), hf_ref.encoder_out(om, mels[1])
+    # golden (minted from the real reference) first: same audio seed 1000
+    step_r, step_c = max(1, ref0.shape[0] // 50), max(1, ref0.shape[1] // 64)
+    assert np.abs(ref0[::step_r, ::step_c] - gold["enc_sub"]).max() < 1e-4
+    for o, r in ((out[0], ref0), (out[1], ref1)):
+        err = np.abs(o - r)
+        # final LayerNorm output has unit scale; bf16 activations through 2-3 layers with gain-8 weights
+        assert err.max() < 0.15 and err.mean() < 0.012, (tag, impl, err.max(), err.mean())
+
+
+@pytest.mark.parametrize("tag", ["tiny10", "small30"])
+def test_teacher_forced_logits_and_greedy(cuda, tag):
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    meta, gold, model = _model_case(tag)
+    chunk = meta["chunk_s"]
+    eng = _engine(model, chunk, max_audios=1)
+    fe = S.make_feature_extractor(chunk)
+    audio = S.synth_audio(chunk, seed=1000)
+    mel = hf_ref.logmel(fe, audio)
+    eng.set_mel(torch.from_numpy(mel[None]))
+    eng.encode(1)
+    om = _oracle_model(model, chunk)
+    # ---- teacher-forced logits at every position against the golden top-8 / strided columns
+    ids = gold["tf_ids"].astype(np.int32)
+    opts = _opts(model)
+    eng.decode_begin(ids[None, :], 1, 1, opts)  # whole sequence is "prompt": nothing is sampled
+    sigma = float(gold["tf_cols"].std())
+    worst = 0.0
+    for t in range(len(ids)):
+        eng.decode_run(1)
+        lg = eng.logits()[0].cpu().numpy()
+        worst = max(worst, np.abs(lg[::997] - gold["tf_cols"][t]).max())
+        top = gold["tf_top_ids"][t]
+        assert np.abs(lg[top] - gold["tf_top_vals"][t]).max() < 0.03 * sigma + 1e-3
+    assert worst < 0.03 * sigma + 1e-3, (worst, sigma)
+    tol = 2.0 * worst
+    # ---- free-running greedy: every engine token must be the oracle's argmax given the same prefix, unless the
+    #      oracle's own top-2 margin at that step is below the measured logit tolerance
+    prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]], dtype=np.int32)
+    gen, toks, n = eng.greedy(prompt, 1, opts, max_new_tokens=32)
+    gen = gen[0]
+    assert len(gen) >= 1
+    full = prompt[0].tolist() + gen.tolist()
+    ref_lg = hf_ref.teacher_forced_logits(om, mel, full)
+    sup = list(model.generation_config.suppress_tokens)
+    near_ties = 0
+    for i, tok in enumerate(gen):
+        row = ref_lg[3 + i].copy()
+        row[sup] = -np.inf
+        if i == 0:
+            row[list(model.generation_config.begin_suppress_tokens)] = -np.inf
+        order = np.argsort(-row)[:2]
+        margin = row[order[0]] - row[order[1]]
+        if tok != order[0]:
+            assert margin < tol and tok == order[1], (i, tok, order, margin, tol)
+            near_ties += 1
+    assert near_ties <= 2
+    # golden greedy tokens from the real reference
+    g = gold["greedy_tokens"]
+    g = g[g != S.EOS]
+    if near_ties == 0:
+        assert gen.tolist() == g[: len(gen)].tolist()
+
+
+def test_batch_rows_agree(cuda):
+    """B=3 audios decoded together give the tokens of the B=1 runs (batched gemv/cross-attention paths)."""
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    meta, gold, model = _model_case("tiny10")
+    eng = _engine(model, 10, max_audios=3)
+    fe = S.make_feature_extractor(10)
+    mels = np.stack([hf_ref.logmel(fe, S.synth_audio(10, seed=s)) for s in (1000, 1001, 1002)])
+    opts = _opts(model)
+    prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]] * 3, dtype=np.int32)
+    eng.set_mel(torch.from_numpy(mels))
+    eng.encode(3)
+    gen3, _, _ = eng.greedy(prompt, 3, opts, max_new_tokens=16)
+    for i in range(3):
+        eng.set_mel(torch.from_numpy(mels[i:i + 1]))
+        eng.encode(1)
+        gen1, _, _ = eng.greedy(prompt[:1], 1, opts, max_new_tokens=16)
+        assert gen1[0].tolist() == gen3[i].tolist(), i

@@ -1,0 +1,148 @@
+"""Single-kernel parity (B200): each CUDA kernel, called through the C-ABI, against a plain torch fp32 reference of the
+same op on the same inputs.  Tolerances are stated per test; operands are bf16 so the reference is computed from the
+bf16-rounded values in fp32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from thewhisper_b200 import _lib
+
+    return _lib, _lib.load()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _gemm(A, W, bias=None, alpha=1.0, act=0, residual=None, out_f32=True, impl=0, force_bn=0):
+    L, lib = _lib()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=A.device)
+    L.check(lib.bw_op_gemm(_ptr(A), _ptr(W), M, N, K, _ptr(bias), alpha, act, _ptr(residual), _ptr(out), int(out_f32), impl,
+                           force_bn, _stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+def _ref_gemm(A, W, bias=None, alpha=1.0, act=0, residual=None):
+    y = A.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias
+    y = y * alpha
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+@pytest.mark.parametrize("impl,bn", [(1, 0), (0, 128), (0, 64), (0, 256), (0, 0)], ids=["simt", "tc128", "tc64", "tc256", "tcauto"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1500, 1280, 1280), (77, 384, 5120), (3000, 3840, 384)])
+def test_gemm_plain(cuda, impl, bn, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    out = _gemm(A, W, impl=impl, force_bn=bn)
+    ref = _ref_gemm(A, W)
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp32 accumulation of exact bf16 products: only summation-order noise
+    assert err <= 2e-3 * max(scale, 1.0), (impl, bn, M, N, K, err, scale)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tc"])
+def test_gemm_epilogues(cuda, impl):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, N, K = 300, 640, 256
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    out = _gemm(A, W, bias=bias, alpha=0.125, act=0, residual=None, impl=impl)
+    assert (out - _ref_gemm(A, W, bias, 0.125)).abs().max().item() < 2e-3
+    out = _gemm(A, W, bias=bias, act=1, impl=impl)
+    assert (out - _ref_gemm(A, W, bias, 1.0, 1)).abs().max().item() < 2e-3
+    out = _gemm(A, W, bias=bias, residual=res, impl=impl)
+    assert (out - _ref_gemm(A, W, bias, 1.0, 0, res)).abs().max().item() < 2e-3
+    outb = _gemm(A, W, bias=bias, act=1, out_f32=False, impl=impl)
+    ref = _ref_gemm(A, W, bias, 1.0, 1)
+    assert (outb.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())  # one bf16 rounding
+    # in-place residual (x += A W^T + b), as the encoder layers use it
+    x = res.clone()
+    L, lib = _lib()
+    L.check(lib.bw_op_gemm(_ptr(A), _ptr(W), M, N, K, _ptr(bias), 1.0, 0, _ptr(x), _ptr(x), 1, impl, 0, _stream()))
+    torch.cuda.synchronize()
+    assert (x - _ref_gemm(A, W, bias, 1.0, 0, res)).abs().max().item() < 2e-3
+
+
+def _ref_attn(qkv, B, S, H):
+    D = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    w = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1)
+    return (w @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tc"])
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 500, 2), (2, 333, 2), (1, 1500, 4)])
+def test_attn_enc(cuda, impl, B, S, H):
+    L, lib = _lib()
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + S + H)
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, generator=g) * 1.5).to(torch.bfloat16).to(cuda)
+    out = torch.zeros((B * S, D), dtype=torch.bfloat16, device=cuda)
+    Spad = (S + 7) // 8 * 8
+    vt = torch.zeros((B, H, 64, Spad), dtype=torch.bfloat16, device=cuda)
+    L.check(lib.bw_op_attn_enc(_ptr(qkv), _ptr(vt), _ptr(out), B, S, H, impl, _stream()))
+    torch.cuda.synchronize()
+    ref = _ref_attn(qkv, B, S, H)
+    err = (out.float() - ref).abs().max().item()
+    # bf16 probabilities + bf16 output: ~2^-8 relative on O(1) values
+    assert err < 3e-2, (impl, B, S, H, err)
+    assert (out.float() - ref).abs().mean().item() < 3e-3
+
+
+def test_layernorm(cuda):
+    L, lib = _lib()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    rows, D = 37, 1280
+    x = (torch.randn(rows, D, generator=g) * 3 + 1).to(cuda)
+    gam = torch.randn(D, generator=g).to(cuda)
+    bet = torch.randn(D, generator=g).to(cuda)
+    ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-5)
+    o32 = torch.empty_like(x)
+    L.check(lib.bw_op_layernorm(_ptr(x), _ptr(gam), _ptr(bet), _ptr(o32), 1, rows, D, _stream()))
+    o16 = torch.empty((rows, D), dtype=torch.bfloat16, device=cuda)
+    L.check(lib.bw_op_layernorm(_ptr(x), _ptr(gam), _ptr(bet), _ptr(o16), 0, rows, D, _stream()))
+    torch.cuda.synchronize()
+    assert (o32 - ref).abs().max().item() < 1e-4
+    assert (o16.float() - ref).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("N,K,ln", [(1280, 1280, True), (5120, 1280, True), (1280, 5120, False), (51866, 1280, True), (130, 128, False)])
+def test_gemv(cuda, M, N, K, ln):
+    L, lib = _lib()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g) * 2 + 0.5).to(cuda)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    gam = torch.randn(K, generator=g).to(cuda) if ln else None
+    bet = torch.randn(K, generator=g).to(cuda) if ln else None
+    out = torch.empty((M, N), dtype=torch.float32, device=cuda)
+    L.check(lib.bw_op_gemv(_ptr(x), _ptr(gam), _ptr(bet), _ptr(W), M, N, K, _ptr(bias), 1.0, 1, _ptr(res), _ptr(out), _stream()))
+    torch.cuda.synchronize()
+    xin = torch.nn.functional.layer_norm(x, (K,), gam, bet, 1e-5) if ln else x
+    ref = torch.nn.functional.gelu(xin @ W.float().t() + bias) + res
+    assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K)

@@ -1,0 +1,663 @@
+// C-ABI (include/thewhisper_b200.h) and the engine that sequences the kernels: encoder pass, cross-K/V projection,
+// CUDA-graph decode steps.  Host C++ only orchestrates; all arithmetic is in the .cu kernels of this directory.
+#include <limits.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/thewhisper_b200.h"
+#include "decode.cuh"
+#include "kernels.h"
+
+namespace bw {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int word_timestamps_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, int audio, int n_tokens, int num_frames,
+                           float time_precision, float* work, float* out_dev);  // timestamps.cu
+
+namespace {
+
+struct EncLayer {
+  const float *ln1g, *ln1b, *bqkv, *bo, *ln2g, *ln2b, *b1, *b2;
+  const bf16 *wqkv, *wo, *w1, *w2;
+};
+struct DecLayer {
+  const float *ln1g, *ln1b, *bqkv, *bo, *ln2g, *ln2b, *xbq, *xbv, *xbo, *ln3g, *ln3b, *b1, *b2;
+  const bf16 *wqkv, *wo, *xwq, *xwk, *xwv, *xwo, *w1, *w2;
+};
+
+struct GraphKey {
+  int A, G, begin_index, ts_rules, align;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(A, G, begin_index, ts_rules, align) < std::tie(o.A, o.G, o.begin_index, o.ts_rules, o.align);
+  }
+};
+
+}  // namespace
+}  // namespace bw
+
+using namespace bw;
+
+struct bw_engine {
+  bw_config cfg;
+  std::map<std::string, const void*> tensors;
+  bool finalized = false;
+  int D, H, S, F, V, Tmax, Spad;
+  // resolved weights
+  const bf16 *conv1_w = nullptr, *conv2_w = nullptr, *embed = nullptr;
+  const float *conv1_b = nullptr, *conv2_b = nullptr, *enc_pos = nullptr, *enc_lnf_g = nullptr, *enc_lnf_b = nullptr;
+  const float *dec_pos = nullptr, *dec_lnf_g = nullptr, *dec_lnf_b = nullptr;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  LogmelPlan* mel_plan = nullptr;
+  std::vector<int> align_pairs;
+  // encoder workspace
+  bf16 *mel_tm = nullptr, *h1 = nullptr, *xn = nullptr, *qkv = nullptr, *vt = nullptr, *ao = nullptr, *hbuf = nullptr, *enc_out = nullptr;
+  float *x_enc = nullptr, *mel_scratch = nullptr;
+  unsigned* mel_max = nullptr;
+  // caches
+  bf16 *cross_k = nullptr, *cross_v = nullptr;  // [L][A][H][S][64]
+  bf16 *self_k = nullptr, *self_v = nullptr;    // [L][Q][Tmax][D]
+  // decoder state
+  int *tokens = nullptr, *finished = nullptr, *pos = nullptr, *anc = nullptr, *anc_tmp = nullptr, *head_slots = nullptr;
+  unsigned *done_ctr = nullptr, *xcounters = nullptr, *sup_bits = nullptr, *bsup_bits = nullptr;
+  float *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dq = nullptr, *dh = nullptr, *logits = nullptr, *part_o = nullptr,
+        *part_ml = nullptr, *align = nullptr, *lse = nullptr, *ts_work = nullptr, *ts_out = nullptr;
+  int *reorder_tmp = nullptr;
+  size_t align_bytes = 0;
+  // current decode session
+  int A = 0, G = 1, Q = 0;
+  bw_decode_opts opts{};
+  bool use_anc = false;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  cudaGraphExec_t cur_graph = nullptr;
+  bool no_graph = false, simt = false;
+  std::map<std::string, std::pair<void*, size_t>> buffers;
+};
+
+namespace bw_api {
+
+template <typename T>
+int dalloc(bw_engine* e, const char* name, T** p, size_t count, bool zero = true) {
+  const size_t bytes = count * sizeof(T);
+  BW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16));
+  if (zero) BW_CUDA_OK(cudaMemset(*p, 0, bytes ? bytes : 16));
+  e->buffers[name] = std::make_pair(static_cast<void*>(*p), bytes);
+  return 0;
+}
+
+template <typename T>
+int need(bw_engine* e, const std::string& name, const T** out) {
+  auto it = e->tensors.find(name);
+  BW_CHECK(it != e->tensors.end() && it->second != nullptr, "weight '%s' is not bound", name.c_str());
+  *out = static_cast<const T*>(it->second);
+  return 0;
+}
+
+int gemm(bw_engine* e, cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi) {
+  return e->simt ? gemm_simt(st, a, W, B, rows, N, K, epi) : gemm_tc(st, a, W, B, rows, N, K, epi, 0);
+}
+
+GemmA plainA(const bf16* base, int rows, int K) {
+  GemmA a;
+  a.base = base;
+  a.batch_stride = (long long)rows * K;
+  a.pitch = K;
+  a.rows_base = rows;
+  a.kwrap = INT_MAX;
+  return a;
+}
+
+GemmEpi plainEpi(int rows, int ld) {
+  GemmEpi ep;
+  ep.batch_stride = (long long)rows * ld;
+  ep.row_stride = ld;
+  ep.head_stride = 64;
+  return ep;
+}
+
+int encode_impl(bw_engine* e, int B, cudaStream_t st) {
+  const int D = e->D, S = e->S, F = e->F, H = e->H, ffn = e->cfg.ffn, nm = e->cfg.n_mels;
+  // ---- conv stem as two wrapping-coordinate GEMMs (modeling_whisper.py:619-625)
+  {
+    GemmA a;
+    a.base = e->mel_tm; a.batch_stride = (long long)(F + 2) * nm; a.pitch = nm; a.rows_base = F + 2; a.kwrap = nm;
+    GemmEpi ep;
+    ep.bias = e->conv1_b; ep.act = 1;
+    ep.out_bf16 = e->h1 + D;  // row t -> padded row t+1
+    ep.batch_stride = (long long)(F + 2) * D; ep.row_stride = D;
+    if (int rc = gemm(e, st, a, e->conv1_w, B, F, D, 3 * nm, ep)) return rc;
+  }
+  {
+    GemmA a;
+    a.base = e->h1; a.batch_stride = (long long)(F + 2) * D; a.pitch = 2 * D; a.rows_base = (F + 2) / 2; a.kwrap = 2 * D;
+    GemmEpi ep;
+    ep.bias = e->conv2_b; ep.act = 1; ep.pos = e->enc_pos;
+    ep.out_f32 = e->x_enc;
+    ep.batch_stride = (long long)S * D; ep.row_stride = D;
+    if (int rc = gemm(e, st, a, e->conv2_w, B, S, D, 3 * D, ep)) return rc;
+  }
+  const float scale = 0.125f;  // head_dim^-1/2, head_dim = 64 (applied inside the attention kernels)
+  (void)scale;
+  for (size_t l = 0; l < e->enc.size(); ++l) {
+    const EncLayer& L = e->enc[l];
+    if (int rc = layernorm_bf16(st, e->x_enc, L.ln1g, L.ln1b, e->xn, B * S, D)) return rc;
+    {
+      GemmEpi ep = plainEpi(S, 3 * D);
+      ep.bias = L.bqkv; ep.out_bf16 = e->qkv;
+      if (int rc = gemm(e, st, plainA(e->xn, S, D), L.wqkv, B, S, 3 * D, D, ep)) return rc;
+    }
+    if (e->simt) {
+      if (int rc = attn_enc_simt(st, e->qkv, e->ao, B, S, H)) return rc;
+    } else {
+      if (int rc = transpose_v(st, e->qkv, e->vt, B, S, e->Spad, H)) return rc;
+      if (int rc = attn_enc_tc(st, e->qkv, e->vt, e->ao, B, S, e->Spad, H)) return rc;
+    }
+    {
+      GemmEpi ep = plainEpi(S, D);
+      ep.bias = L.bo; ep.residual = e->x_enc; ep.out_f32 = e->x_enc;
+      if (int rc = gemm(e, st, plainA(e->ao, S, D), L.wo, B, S, D, D, ep)) return rc;
+    }
+    if (int rc = layernorm_bf16(st, e->x_enc, L.ln2g, L.ln2b, e->xn, B * S, D)) return rc;
+    {
+      GemmEpi ep = plainEpi(S, ffn);
+      ep.bias = L.b1; ep.act = 1; ep.out_bf16 = e->hbuf;
+      if (int rc = gemm(e, st, plainA(e->xn, S, D), L.w1, B, S, ffn, D, ep)) return rc;
+    }
+    {
+      GemmEpi ep = plainEpi(S, D);
+      ep.bias = L.b2; ep.residual = e->x_enc; ep.out_f32 = e->x_enc;
+      if (int rc = gemm(e, st, plainA(e->hbuf, S, ffn), L.w2, B, S, D, ffn, ep)) return rc;
+    }
+  }
+  if (int rc = layernorm_bf16(st, e->x_enc, e->enc_lnf_g, e->enc_lnf_b, e->enc_out, B * S, D)) return rc;
+  // ---- cross-attention K/V of every decoder layer, written head-major: [L][A][H][S][64]
+  const long long per_layer = (long long)e->cfg.max_audios * H * S * 64;
+  for (size_t l = 0; l < e->dec.size(); ++l) {
+    const DecLayer& L = e->dec[l];
+    GemmEpi ep;
+    ep.batch_stride = (long long)H * S * 64; ep.row_stride = 64; ep.head_stride = (long long)S * 64;
+    ep.out_bf16 = e->cross_k + l * per_layer;
+    if (int rc = gemm(e, st, plainA(e->enc_out, S, D), L.xwk, B, S, D, D, ep)) return rc;
+    ep.bias = L.xbv;
+    ep.out_bf16 = e->cross_v + l * per_layer;
+    if (int rc = gemm(e, st, plainA(e->enc_out, S, D), L.xwv, B, S, D, D, ep)) return rc;
+  }
+  return 0;
+}
+
+// one decoder step for all Q sequences (enqueued on st; captured into a CUDA graph by the caller)
+int step_impl(bw_engine* e, cudaStream_t st) {
+  const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, V = e->V, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
+  if (int rc = launch_embed(st, e->embed, e->dec_pos, e->tokens, e->pos, e->dx, Q, D, Tmax)) return rc;
+  const long long self_layer = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
+  const long long cross_layer = (long long)e->cfg.max_audios * H * S * 64;
+  for (size_t l = 0; l < e->dec.size(); ++l) {
+    const DecLayer& L = e->dec[l];
+    bf16* kc = e->self_k + l * self_layer;
+    bf16* vc = e->self_v + l * self_layer;
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN1 + fused QKV projection (+ self-KV append)
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln1g; g.ln_b = L.ln1b;
+      g.W = L.wqkv; g.N = 3 * D; g.K = D; g.bias = L.bqkv; g.alpha = 0.125f; g.alpha_cols = D;
+      g.out = e->dqkv + (long long)m0 * 3 * D; g.ldo = 3 * D;
+      g.kc = kc; g.vc = vc; g.D = D; g.Tmax = Tmax; g.seq0 = m0; g.pos = e->pos;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+    {
+      SelfAttnArgs s;
+      s.qkv = e->dqkv; s.kc = kc; s.vc = vc; s.anc = e->use_anc ? e->anc : nullptr; s.out = e->dattn; s.pos = e->pos;
+      s.H = H; s.D = D; s.Tmax = Tmax;
+      if (int rc = launch_self_attn(st, s, Q)) return rc;
+    }
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // out-proj + residual
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dattn + (long long)m0 * D; g.ldx = D; g.W = L.wo; g.N = D; g.K = D; g.bias = L.bo;
+      g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN2 + cross q projection
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln2g; g.ln_b = L.ln2b;
+      g.W = L.xwq; g.N = D; g.K = D; g.bias = L.xbq; g.alpha = 0.125f; g.alpha_cols = D;
+      g.out = e->dq + (long long)m0 * D; g.ldo = D;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+    {
+      CrossAttnArgs c;
+      c.q = e->dq; c.kc = e->cross_k + l * cross_layer; c.vc = e->cross_v + l * cross_layer; c.out = e->dattn;
+      c.part_o = e->part_o; c.part_ml = e->part_ml; c.counters = e->xcounters;
+      c.S = S; c.H = H; c.D = D; c.G = G; c.pos = e->pos;
+      if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
+        c.align = e->align; c.head_slots = e->head_slots + l * H; c.Ha = e->cfg.n_align_heads;
+        c.Tcap = e->cfg.max_align_steps; c.step_base = e->opts.begin_index;  // row 0 = first generated token as input
+      }
+      if (int rc = launch_cross_attn(st, c, A)) return rc;
+    }
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // cross out-proj + residual
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dattn + (long long)m0 * D; g.ldx = D; g.W = L.xwo; g.N = D; g.K = D; g.bias = L.xbo;
+      g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN3 + fc1 + GELU
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln3g; g.ln_b = L.ln3b;
+      g.W = L.w1; g.N = ffn; g.K = D; g.bias = L.b1; g.act = 1;
+      g.out = e->dh + (long long)m0 * ffn; g.ldo = ffn;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+    for (int m0 = 0; m0 < Q; m0 += 8) {  // fc2 + residual
+      GemvArgs g;
+      g.M = std::min(8, Q - m0);
+      g.x = e->dh + (long long)m0 * ffn; g.ldx = ffn; g.W = L.w2; g.N = D; g.K = ffn; g.bias = L.b2;
+      g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
+      if (int rc = launch_gemv(st, g)) return rc;
+    }
+  }
+  for (int m0 = 0; m0 < Q; m0 += 8) {  // final LN + tied LM head
+    GemvArgs g;
+    g.M = std::min(8, Q - m0);
+    g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = e->dec_lnf_g; g.ln_b = e->dec_lnf_b;
+    g.W = e->embed; g.N = V; g.K = D;
+    g.out = e->logits + (long long)m0 * V; g.ldo = V;
+    if (int rc = launch_gemv(st, g)) return rc;
+  }
+  SelectArgs s;
+  s.logits = e->logits; s.V = V; s.Q = Q; s.Tmax = Tmax; s.tokens = e->tokens; s.finished = e->finished; s.pos = e->pos;
+  s.done_ctr = e->done_ctr; s.suppress_bits = e->sup_bits; s.begin_suppress_bits = e->bsup_bits;
+  s.begin_index = e->opts.begin_index; s.eos = e->opts.eos_token; s.pad = e->opts.pad_token;
+  s.ts_rules = e->opts.timestamp_rules; s.ts_begin = e->opts.timestamp_begin; s.no_ts = e->opts.no_timestamps_token;
+  s.max_initial_ts = e->opts.max_initial_timestamp_index; s.out_lse = e->lse;
+  return launch_select(st, s);
+}
+
+__global__ void mel_to_tm_kernel(const float* __restrict__ mel, bf16* __restrict__ out, int n_mels, int frames) {
+  // [B][n_mels][frames] fp32 -> [B][frames+2][n_mels] bf16 (rows 0 and frames+1 zero)
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, f0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, f = f0 + tx;
+    tile[i][tx] = (m < n_mels && f < frames) ? mel[((long long)b * n_mels + m) * frames + f] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int f = f0 + i, m = m0 + tx;
+    if (f < frames && m < n_mels) out[((long long)b * (frames + 2) + f + 1) * n_mels + m] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+__global__ void iota_anc_kernel(int* anc, int Q, int Tmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q * Tmax) anc[i] = i / Tmax;
+}
+
+// new sequence i continues old sequence parent[i]: permute block-table rows, overwrite history + newest token
+__global__ void reorder_kernel(const int* __restrict__ anc_old, int* __restrict__ anc_new, const int* __restrict__ tok_old,
+                               int* __restrict__ tok_new, const int* __restrict__ parent, const int* __restrict__ next_tok,
+                               const int* __restrict__ pos_ptr, int Tmax) {
+  const int i = blockIdx.x;
+  const int p = parent[i];
+  const int cur = *pos_ptr;  // tokens [0, cur] are filled; position cur-1 was the last KV written
+  for (int s = threadIdx.x; s < Tmax; s += blockDim.x) {
+    anc_new[i * Tmax + s] = (s < cur) ? anc_old[p * Tmax + s] : i;
+    int t = tok_old[p * Tmax + s];
+    if (s == cur) t = next_tok[i];
+    tok_new[i * Tmax + s] = t;
+  }
+}
+
+}  // namespace bw_api
+using namespace bw_api;
+
+extern "C" {
+
+const char* bw_last_error(void) { return bw::get_error(); }
+int bw_abi_version(void) { return BW_ABI_VERSION; }
+int bw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int bw_engine_create(const bw_config* cfg, bw_engine** out) {
+  BW_CHECK(cfg && out, "bw_engine_create: null argument");
+  BW_CHECK(cfg->d_model == cfg->n_heads * 64, "head_dim must be 64 (d_model=%d, heads=%d)", cfg->d_model, cfg->n_heads);
+  BW_CHECK(cfg->d_model % 64 == 0 && cfg->ffn % 64 == 0, "d_model and ffn must be multiples of 64");
+  BW_CHECK(cfg->n_mels == 128 || cfg->n_mels == 64, "n_mels=%d unsupported (the conv stem's TMA view needs a multiple of 64)", cfg->n_mels);
+  BW_CHECK(cfg->max_beams >= 1 && cfg->max_beams <= MAXG, "max_beams must be in 1..%d", MAXG);
+  BW_CHECK(cfg->max_source_positions >= 1 && cfg->max_source_positions <= 2048, "max_source_positions out of range");
+  BW_CHECK(bw_device_count() > 0, "no CUDA device: thewhisper_b200 has no CPU fallback");
+  bw_engine* e = new bw_engine();
+  e->cfg = *cfg;
+  e->D = cfg->d_model; e->H = cfg->n_heads; e->S = cfg->max_source_positions; e->F = 2 * e->S; e->V = cfg->vocab;
+  e->Tmax = cfg->max_target_positions; e->Spad = (e->S + 7) / 8 * 8;
+  const char* ng = getenv("BW_NO_GRAPH");
+  e->no_graph = ng && ng[0] == '1';
+  const char* impl = getenv("BW_GEMM_IMPL");
+  e->simt = impl && strcmp(impl, "simt") == 0;
+  *out = e;
+  return 0;
+}
+
+void bw_engine_destroy(bw_engine* e) {
+  if (!e) return;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : e->buffers) cudaFree(kv.second.first);
+  logmel_plan_destroy(e->mel_plan);
+  delete e;
+}
+
+int bw_engine_set_tensor(bw_engine* e, const char* name, const void* p) {
+  BW_CHECK(e && name && p, "bw_engine_set_tensor: null argument");
+  BW_CHECK(!e->finalized, "bw_engine_set_tensor after finalize");
+  e->tensors[name] = p;
+  return 0;
+}
+
+int bw_engine_set_mel_filters(bw_engine* e, const float* bank_host) {
+  BW_CHECK(e && bank_host, "bw_engine_set_mel_filters: null argument");
+  logmel_plan_destroy(e->mel_plan);
+  e->mel_plan = nullptr;
+  return logmel_plan_create_from_bank(&e->mel_plan, bank_host, e->cfg.n_mels);
+}
+
+int bw_engine_set_alignment_heads(bw_engine* e, const int32_t* pairs, int32_t n) {
+  BW_CHECK(e && (pairs || n == 0), "bw_engine_set_alignment_heads: null argument");
+  BW_CHECK(n == e->cfg.n_align_heads, "alignment heads: got %d pairs, config says %d", n, e->cfg.n_align_heads);
+  e->align_pairs.assign(pairs, pairs + 2 * n);
+  return 0;
+}
+
+int bw_engine_finalize(bw_engine* e) {
+  BW_CHECK(e && !e->finalized, "bw_engine_finalize: bad engine");
+  const bw_config& c = e->cfg;
+  const int D = e->D, S = e->S, F = e->F, H = e->H, V = e->V, Tmax = e->Tmax, A = c.max_audios, Qm = c.max_audios * c.max_beams;
+#define NEED(T, field, name) if (int rc = need<T>(e, name, &field)) return rc;
+  NEED(bf16, e->conv1_w, "enc.conv1.w") NEED(float, e->conv1_b, "enc.conv1.b")
+  NEED(bf16, e->conv2_w, "enc.conv2.w") NEED(float, e->conv2_b, "enc.conv2.b")
+  NEED(float, e->enc_pos, "enc.pos") NEED(float, e->enc_lnf_g, "enc.lnf.g") NEED(float, e->enc_lnf_b, "enc.lnf.b")
+  NEED(bf16, e->embed, "dec.embed") NEED(float, e->dec_pos, "dec.pos")
+  NEED(float, e->dec_lnf_g, "dec.lnf.g") NEED(float, e->dec_lnf_b, "dec.lnf.b")
+  e->enc.resize(c.enc_layers);
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const std::string p = "enc." + std::to_string(i) + ".";
+    EncLayer& L = e->enc[i];
+    NEED(float, L.ln1g, p + "ln1.g") NEED(float, L.ln1b, p + "ln1.b") NEED(bf16, L.wqkv, p + "wqkv") NEED(float, L.bqkv, p + "bqkv")
+    NEED(bf16, L.wo, p + "wo") NEED(float, L.bo, p + "bo") NEED(float, L.ln2g, p + "ln2.g") NEED(float, L.ln2b, p + "ln2.b")
+    NEED(bf16, L.w1, p + "w1") NEED(float, L.b1, p + "b1") NEED(bf16, L.w2, p + "w2") NEED(float, L.b2, p + "b2")
+  }
+  e->dec.resize(c.dec_layers);
+  for (int i = 0; i < c.dec_layers; ++i) {
+    const std::string p = "dec." + std::to_string(i) + ".";
+    DecLayer& L = e->dec[i];
+    NEED(float, L.ln1g, p + "ln1.g") NEED(float, L.ln1b, p + "ln1.b") NEED(bf16, L.wqkv, p + "wqkv") NEED(float, L.bqkv, p + "bqkv")
+    NEED(bf16, L.wo, p + "wo") NEED(float, L.bo, p + "bo") NEED(float, L.ln2g, p + "ln2.g") NEED(float, L.ln2b, p + "ln2.b")
+    NEED(bf16, L.xwq, p + "xwq") NEED(float, L.xbq, p + "xbq") NEED(bf16, L.xwk, p + "xwk") NEED(bf16, L.xwv, p + "xwv")
+    NEED(float, L.xbv, p + "xbv") NEED(bf16, L.xwo, p + "xwo") NEED(float, L.xbo, p + "xbo")
+    NEED(float, L.ln3g, p + "ln3.g") NEED(float, L.ln3b, p + "ln3.b")
+    NEED(bf16, L.w1, p + "w1") NEED(float, L.b1, p + "b1") NEED(bf16, L.w2, p + "w2") NEED(float, L.b2, p + "b2")
+  }
+#undef NEED
+  BW_CHECK(e->mel_plan != nullptr, "mel filter bank not set (bw_engine_set_mel_filters)");
+  const size_t BS = (size_t)A * S;
+  if (dalloc(e, "mel_tm", &e->mel_tm, (size_t)A * (F + 2) * c.n_mels)) return -1;
+  if (dalloc(e, "mel_scratch", &e->mel_scratch, (size_t)A * F * c.n_mels)) return -1;
+  if (dalloc(e, "mel_max", &e->mel_max, (size_t)A)) return -1;
+  if (dalloc(e, "h1", &e->h1, (size_t)A * (F + 2) * D)) return -1;
+  if (dalloc(e, "x_enc", &e->x_enc, BS * D)) return -1;
+  if (dalloc(e, "xn", &e->xn, BS * D)) return -1;
+  if (dalloc(e, "qkv", &e->qkv, BS * 3 * D)) return -1;
+  if (dalloc(e, "vt", &e->vt, (size_t)A * H * 64 * e->Spad)) return -1;
+  if (dalloc(e, "ao", &e->ao, BS * D)) return -1;
+  if (dalloc(e, "hbuf", &e->hbuf, BS * c.ffn)) return -1;
+  if (dalloc(e, "enc_out", &e->enc_out, BS * D)) return -1;
+  if (dalloc(e, "cross_k", &e->cross_k, (size_t)c.dec_layers * A * H * S * 64, false)) return -1;
+  if (dalloc(e, "cross_v", &e->cross_v, (size_t)c.dec_layers * A * H * S * 64, false)) return -1;
+  if (dalloc(e, "self_k", &e->self_k, (size_t)c.dec_layers * Qm * Tmax * D, false)) return -1;
+  if (dalloc(e, "self_v", &e->self_v, (size_t)c.dec_layers * Qm * Tmax * D, false)) return -1;
+  if (dalloc(e, "tokens", &e->tokens, (size_t)Qm * Tmax)) return -1;
+  if (dalloc(e, "tokens_tmp", &e->reorder_tmp, (size_t)Qm * Tmax + 2 * Qm)) return -1;
+  if (dalloc(e, "finished", &e->finished, (size_t)Qm)) return -1;
+  if (dalloc(e, "pos", &e->pos, 1)) return -1;
+  if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
+  if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
+  if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
+  if (dalloc(e, "xcounters", &e->xcounters, (size_t)A * H)) return -1;
+  if (dalloc(e, "sup_bits", &e->sup_bits, (size_t)(V + 31) / 32)) return -1;
+  if (dalloc(e, "bsup_bits", &e->bsup_bits, (size_t)(V + 31) / 32)) return -1;
+  if (dalloc(e, "dx", &e->dx, (size_t)Qm * D)) return -1;
+  if (dalloc(e, "dqkv", &e->dqkv, (size_t)Qm * 3 * D)) return -1;
+  if (dalloc(e, "dattn", &e->dattn, (size_t)Qm * D)) return -1;
+  if (dalloc(e, "dq", &e->dq, (size_t)Qm * D)) return -1;
+  if (dalloc(e, "dh", &e->dh, (size_t)Qm * c.ffn)) return -1;
+  if (dalloc(e, "logits", &e->logits, (size_t)Qm * V)) return -1;
+  if (dalloc(e, "lse", &e->lse, (size_t)Qm)) return -1;
+  if (dalloc(e, "part_o", &e->part_o, (size_t)A * H * XSPLIT * c.max_beams * 64)) return -1;
+  if (dalloc(e, "part_ml", &e->part_ml, (size_t)A * H * XSPLIT * c.max_beams * 2)) return -1;
+  if (dalloc(e, "head_slots", &e->head_slots, (size_t)c.dec_layers * H)) return -1;
+  {
+    std::vector<int> hs((size_t)c.dec_layers * H, -1);
+    for (int i = 0; i < c.n_align_heads && 2 * i + 1 < (int)e->align_pairs.size(); ++i) {
+      const int l = e->align_pairs[2 * i], h = e->align_pairs[2 * i + 1];
+      BW_CHECK(l >= 0 && l < c.dec_layers && h >= 0 && h < H, "alignment head (%d,%d) out of range", l, h);
+      hs[(size_t)l * H + h] = i;
+    }
+    BW_CUDA_OK(cudaMemcpy(e->head_slots, hs.data(), hs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  if (c.n_align_heads > 0) {
+    BW_CHECK((int)e->align_pairs.size() == 2 * c.n_align_heads, "alignment heads not set");
+    if (dalloc(e, "align", &e->align, (size_t)A * c.n_align_heads * c.max_align_steps * S)) return -1;
+    if (dalloc(e, "ts_work", &e->ts_work, (size_t)2 * c.n_align_heads * c.max_align_steps * S + (size_t)(c.max_align_steps + 2) * (S + 2) * 3 + 4096)) return -1;
+    if (dalloc(e, "ts_out", &e->ts_out, (size_t)c.max_align_steps + 8)) return -1;
+  }
+  e->finalized = true;
+  return 0;
+}
+
+int bw_engine_buffer(bw_engine* e, const char* name, void** p, size_t* bytes) {
+  BW_CHECK(e && name && p, "bw_engine_buffer: null argument");
+  auto it = e->buffers.find(name);
+  BW_CHECK(it != e->buffers.end(), "bw_engine_buffer: unknown buffer '%s'", name);
+  *p = it->second.first;
+  if (bytes) *bytes = it->second.second;
+  return 0;
+}
+
+int bw_logmel(bw_engine* e, const float* pcm, int32_t B, int32_t n_samples, float* mel_f32_out, void* stream) {
+  BW_CHECK(e && e->finalized && pcm, "bw_logmel: bad arguments");
+  BW_CHECK(B >= 1 && B <= e->cfg.max_audios, "bw_logmel: B=%d outside 1..%d", B, e->cfg.max_audios);
+  BW_CHECK(n_samples == e->F * 160, "bw_logmel: n_samples=%d, expected %d for this chunk length", n_samples, e->F * 160);
+  return logmel(static_cast<cudaStream_t>(stream), e->mel_plan, pcm, B, n_samples, e->F, e->mel_tm, mel_f32_out, e->mel_scratch, e->mel_max);
+}
+
+int bw_set_mel(bw_engine* e, const float* mel, int32_t B, void* stream) {
+  BW_CHECK(e && e->finalized && mel, "bw_set_mel: bad arguments");
+  BW_CHECK(B >= 1 && B <= e->cfg.max_audios, "bw_set_mel: B=%d outside 1..%d", B, e->cfg.max_audios);
+  dim3 grid((e->F + 31) / 32, (e->cfg.n_mels + 31) / 32, B);
+  mel_to_tm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, e->mel_tm, e->cfg.n_mels, e->F);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bw_encode(bw_engine* e, int32_t B, void* stream) {
+  BW_CHECK(e && e->finalized, "bw_encode: engine not finalized");
+  BW_CHECK(B >= 1 && B <= e->cfg.max_audios, "bw_encode: B=%d outside 1..%d", B, e->cfg.max_audios);
+  return encode_impl(e, B, static_cast<cudaStream_t>(stream));
+}
+
+int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, int32_t plen, const bw_decode_opts* opts, void* stream) {
+  BW_CHECK(e && e->finalized && prompt && opts, "bw_decode_begin: bad arguments");
+  BW_CHECK(A >= 1 && A <= e->cfg.max_audios && G >= 1 && G <= e->cfg.max_beams, "bw_decode_begin: A=%d G=%d out of range", A, G);
+  BW_CHECK(plen >= 1 && plen <= e->Tmax, "bw_decode_begin: prompt_len=%d out of range", plen);
+  BW_CHECK(opts->begin_index >= 1 && opts->begin_index <= plen, "bw_decode_begin: begin_index=%d outside 1..prompt_len", opts->begin_index);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  e->A = A; e->G = G; e->Q = A * G; e->opts = *opts; e->use_anc = G > 1;
+  const int Q = e->Q, Tmax = e->Tmax, V = e->V;
+  std::vector<int> tok((size_t)Q * Tmax, opts->pad_token);
+  for (int q = 0; q < Q; ++q) memcpy(&tok[(size_t)q * Tmax], prompt + (size_t)q * plen, sizeof(int) * plen);
+  BW_CUDA_OK(cudaMemcpyAsync(e->tokens, tok.data(), tok.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  std::vector<unsigned> bits((V + 31) / 32, 0u), bbits((V + 31) / 32, 0u);
+  for (int i = 0; i < opts->n_suppress; ++i) {
+    const int t = opts->suppress_tokens[i];
+    if (t >= 0 && t < V) bits[t >> 5] |= 1u << (t & 31);
+  }
+  for (int i = 0; i < opts->n_begin_suppress; ++i) {
+    const int t = opts->begin_suppress_tokens[i];
+    if (t >= 0 && t < V) bbits[t >> 5] |= 1u << (t & 31);
+  }
+  BW_CUDA_OK(cudaMemcpyAsync(e->sup_bits, bits.data(), bits.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  BW_CUDA_OK(cudaMemcpyAsync(e->bsup_bits, bbits.data(), bbits.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  BW_CUDA_OK(cudaMemsetAsync(e->finished, 0, sizeof(int) * Q, st));
+  BW_CUDA_OK(cudaMemsetAsync(e->pos, 0, sizeof(int), st));
+  BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
+  BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
+  iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
+  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  e->cur_graph = nullptr;
+  if (!e->no_graph) {
+    GraphKey key{A, G, opts->begin_index, opts->timestamp_rules * 4 + (opts->max_initial_timestamp_index + 1) * 8, opts->record_alignment};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      cudaStream_t cs;
+      BW_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      BW_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int rc = step_impl(e, cs);
+      const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      if (rc != 0 || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (rc == 0) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        return -1;
+      }
+      cudaGraphExec_t exec = nullptr;
+      BW_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+      it = e->graphs.emplace(key, exec).first;
+    }
+    e->cur_graph = it->second;
+  }
+  return 0;
+}
+
+int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream) {
+  BW_CHECK(e && e->finalized && e->Q > 0, "bw_decode_run: no decode in progress");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_steps; ++i) {
+    if (e->cur_graph) {
+      BW_CUDA_OK(cudaGraphLaunch(e->cur_graph, st));
+    } else {
+      if (int rc = step_impl(e, st)) return rc;
+    }
+  }
+  return 0;
+}
+
+int bw_decode_read(bw_engine* e, int32_t* tokens_host, int32_t* finished_host, int32_t* pos_host, void* stream) {
+  BW_CHECK(e && e->finalized && e->Q > 0, "bw_decode_read: no decode in progress");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tokens_host) BW_CUDA_OK(cudaMemcpyAsync(tokens_host, e->tokens, sizeof(int) * e->Q * e->Tmax, cudaMemcpyDeviceToHost, st));
+  if (finished_host) BW_CUDA_OK(cudaMemcpyAsync(finished_host, e->finished, sizeof(int) * e->Q, cudaMemcpyDeviceToHost, st));
+  if (pos_host) BW_CUDA_OK(cudaMemcpyAsync(pos_host, e->pos, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BW_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bw_decode_reorder(bw_engine* e, const int32_t* parent_host, const int32_t* next_token_host, void* stream) {
+  BW_CHECK(e && e->finalized && e->Q > 0 && parent_host && next_token_host, "bw_decode_reorder: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Q = e->Q, Tmax = e->Tmax;
+  int* d_parent = e->reorder_tmp + (size_t)e->cfg.max_audios * e->cfg.max_beams * Tmax;
+  int* d_next = d_parent + Q;
+  BW_CUDA_OK(cudaMemcpyAsync(d_parent, parent_host, sizeof(int) * Q, cudaMemcpyHostToDevice, st));
+  BW_CUDA_OK(cudaMemcpyAsync(d_next, next_token_host, sizeof(int) * Q, cudaMemcpyHostToDevice, st));
+  reorder_kernel<<<Q, 128, 0, st>>>(e->anc, e->anc_tmp, e->tokens, e->reorder_tmp, d_parent, d_next, e->pos, Tmax);
+  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(cudaMemcpyAsync(e->anc, e->anc_tmp, sizeof(int) * Q * Tmax, cudaMemcpyDeviceToDevice, st));
+  BW_CUDA_OK(cudaMemcpyAsync(e->tokens, e->reorder_tmp, sizeof(int) * Q * Tmax, cudaMemcpyDeviceToDevice, st));
+  BW_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision, float* out_host,
+                       void* stream) {
+  BW_CHECK(e && e->finalized && out_host, "bw_word_timestamps: bad arguments");
+  BW_CHECK(e->cfg.n_align_heads > 0 && e->align, "bw_word_timestamps: engine built without alignment heads");
+  BW_CHECK(audio >= 0 && audio < e->cfg.max_audios, "bw_word_timestamps: audio index out of range");
+  BW_CHECK(n_tokens >= 1 && n_tokens <= e->cfg.max_align_steps, "bw_word_timestamps: n_tokens=%d outside 1..%d", n_tokens, e->cfg.max_align_steps);
+  BW_CHECK(num_frames >= 1 && num_frames <= e->S, "bw_word_timestamps: num_frames=%d outside 1..%d", num_frames, e->S);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = word_timestamps_device(st, e->align, e->cfg.n_align_heads, e->cfg.max_align_steps, e->S, audio, n_tokens, num_frames,
+                                      time_precision, e->ts_work, e->ts_out))
+    return rc;
+  BW_CUDA_OK(cudaMemcpyAsync(out_host, e->ts_out, sizeof(float) * (n_tokens + 1), cudaMemcpyDeviceToHost, st));
+  BW_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- single ops -------------------------------------------------------------------------------------------------
+int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,
+               const float* residual, void* out, int32_t out_is_f32, int32_t impl, int32_t force_bn, void* stream) {
+  BW_CHECK(A && W && out, "bw_op_gemm: null pointer");
+  GemmEpi ep = plainEpi(M, N);
+  ep.bias = bias; ep.alpha = alpha; ep.act = act; ep.residual = residual;
+  if (out_is_f32) ep.out_f32 = static_cast<float*>(out);
+  else ep.out_bf16 = static_cast<bf16*>(out);
+  const GemmA a = plainA(static_cast<const bf16*>(A), M, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 1) return gemm_simt(st, a, static_cast<const bf16*>(W), 1, M, N, K, ep);
+  return gemm_tc(st, a, static_cast<const bf16*>(W), 1, M, N, K, ep, force_bn);
+}
+
+int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int32_t S, int32_t H, int32_t impl, void* stream) {
+  BW_CHECK(qkv && out, "bw_op_attn_enc: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 1) return attn_enc_simt(st, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, S, H);
+  BW_CHECK(vt_scratch, "bw_op_attn_enc: vt_scratch required for the tcgen05 path");
+  const int Spad = (S + 7) / 8 * 8;
+  if (int rc = transpose_v(st, static_cast<const bf16*>(qkv), static_cast<bf16*>(vt_scratch), B, S, Spad, H)) return rc;
+  return attn_enc_tc(st, static_cast<const bf16*>(qkv), static_cast<const bf16*>(vt_scratch), static_cast<bf16*>(out), B, S, Spad, H);
+}
+
+int bw_op_layernorm(const float* x, const float* g, const float* b, void* out, int32_t out_is_f32, int32_t rows, int32_t D, void* stream) {
+  BW_CHECK(x && g && b && out, "bw_op_layernorm: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return out_is_f32 ? layernorm_f32(st, x, g, b, static_cast<float*>(out), rows, D)
+                    : layernorm_bf16(st, x, g, b, static_cast<bf16*>(out), rows, D);
+}
+
+int bw_op_gemv(const float* x, const float* ln_g, const float* ln_b, const void* W, int32_t M, int32_t N, int32_t K, const float* bias,
+               float alpha, int32_t act, const float* residual, float* out, void* stream) {
+  BW_CHECK(x && W && out, "bw_op_gemv: null pointer");
+  GemvArgs g;
+  g.x = x; g.ldx = K; g.ln_g = ln_g; g.ln_b = ln_b; g.W = static_cast<const bf16*>(W); g.N = N; g.K = K; g.M = M;
+  g.bias = bias; g.alpha = alpha; g.alpha_cols = (alpha != 1.0f) ? N : 0; g.act = act; g.residual = residual; g.out = out; g.ldo = N;
+  return launch_gemv(static_cast<cudaStream_t>(stream), g);
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// Encoder self-attention (non-causal, head_dim 64) as a tcgen05 flash kernel for sm_100a.
+//
+// Replaces SDPA / eager attention of TF/models/whisper/modeling_whisper.py:215-238,343-353 for the encoder
+// (no mask, :637-641).  softmax(q k^T * dh^-1/2) v with fp32 scores/accumulators, bf16 operands.
+//
+// One CTA = 128 query rows of one (batch, head); 192 threads:
+//   warps 0-3  softmax: one query row per thread.  S tile (128x128 fp32) is read from TMEM with tcgen05.ld,
+//              online max/sum in registers, P (bf16) written to smem in the 128B-swizzled K-major layout the
+//              PV MMA consumes; the PV partial (128x64 fp32) is read back from TMEM and folded into the
+//              running output held in registers (no TMEM read-modify-write).
+//   warp  4    TMA producer: Q once, then K / V^T tiles through a 2-deep ring (mbarrier complete_tx)
+//   warp  5    TMEM allocator + MMA issuer: S = Q K^T (4 x tcgen05.mma, N=128), O_j = P V (8 x, N=64)
+// 112 KB smem and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's exp phase overlaps the other's MMAs.
+// Keys beyond S (tile overrun into the next row block / TMA zero fill) are masked to -inf before the max.
+#include "kernels.h"
+
+namespace bw {
+
+namespace {
+
+constexpr int TQ = 128;   // query rows per CTA
+constexpr int TK = 128;   // keys per tile
+constexpr int DH = 64;
+constexpr int Q_BYTES = TQ * DH * 2;       // 16 KB
+constexpr int K_BYTES = TK * DH * 2;       // 16 KB
+constexpr int V_BYTES = DH * TK * 2;       // 16 KB  (two 8 KB atoms of 64 keys)
+constexpr int P_BYTES = TQ * TK * 2;       // 32 KB  (two 16 KB atoms of 64 keys)
+constexpr int ATT_SMEM = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES + 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnParams {
+  int B, S, H, D;
+  float scale_log2e;  // dh^-1/2 * log2(e)
+  bf16* out;
+};
+
+__global__ void __launch_bounds__(192, 2)
+attn_enc_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + 2 * K_BYTES;
+  uint8_t* sP = sV + 2 * V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* k_empty = bars + 5;  // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int NT = (p.S + TK - 1) / TK;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("[bw] attn_enc: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVT);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;         // columns [0,128)
+  const uint32_t tmem_O = tmem_base + 128;   // columns [128,192)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int row0 = b * p.S;
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tmQK, q_full, h * DH, row0 + q0);
+      for (int j = 0; j < NT; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], K_BYTES);
+        tma_load_2d(sK + s * K_BYTES, &tmQK, &k_full[s], p.D + h * DH, row0 + j * TK);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], V_BYTES);
+        const int vrow = (b * p.H + h) * DH;
+        tma_load_2d(sV + s * V_BYTES, &tmVT, &v_full[s], j * TK, vrow);
+        tma_load_2d(sV + s * V_BYTES + V_BYTES / 2, &tmVT, &v_full[s], j * TK + 64, vrow);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, DH);
+      const uint64_t qd = umma_desc_sw128(smem_u32(sQ));
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t kd = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, qd + 2 * k, kd + 2 * k, idesc_s, (uint32_t)(k != 0));
+        umma_commit(s_full);
+        umma_commit(&k_empty[0]);
+      }
+      for (int j = 0; j < NT; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);  // softmax consumed S(j) and published P(j)
+        mbar_wait(&v_full[s], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          const uint64_t pd = umma_desc_sw128(smem_u32(sP + (k >> 2) * (P_BYTES / 2))) + 2 * (k & 3);
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV + s * V_BYTES + (k >> 2) * (V_BYTES / 2))) + 2 * (k & 3);
+          umma_bf16(tmem_O, pd, vd, idesc_o, (uint32_t)(k != 0));
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[s]);
+        if (j + 1 < NT) {
+          const int s2 = (j + 1) & 1;
+          mbar_wait(&k_full[s2], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK + s2 * K_BYTES));
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_S, qd + 2 * k, kd + 2 * k, idesc_s, (uint32_t)(k != 0));
+          umma_commit(s_full);
+          umma_commit(&k_empty[s2]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / output warps ------------------------------
+    const int r = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = 0.f;
+    for (int j = 0; j < NT; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int key0 = j * TK;
+      // pass 1: row max over the valid keys of this tile
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_wait();
+        const int kbase = key0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + i < p.S) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, tmax);                     // finite: every tile has >= 1 valid key
+      const float alpha = exp2f((m - m_new) * p.scale_log2e);  // m = -inf on the first tile -> 0
+      const float mb = m_new * p.scale_log2e;
+      float lsum = 0.f;
+      // pass 2: p = exp2(s*c - m*c), bf16 P into the swizzled A-operand layout
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
+        tmem_ld_wait();
+        const int kbase = key0 + c * 32;
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
+          pf[i] = (kbase + i < p.S) ? e : 0.f;
+          lsum += pf[i];
+        }
+        uint8_t* atom = sP + (c >> 1) * (P_BYTES / 2) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
+          w.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
+          w.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
+          w.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) = w;
+        }
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      fence_proxy_async_smem();  // P visible to the tensor core's async-proxy reads
+      tc_fence_before();         // our tcgen05.ld of S are complete before the issuer overwrites S
+      mbar_arrive(p_full);
+      // fold PV(j) into the running output
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_sel + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(v[i]));
+      }
+    }
+    const int q = q0 + r;
+    if (q < p.S) {
+      const float inv = 1.0f / l;
+      bf16* op = p.out + ((long long)(b * p.S + q) * p.D + h * DH);
+#pragma unroll
+      for (int i = 0; i < DH; i += 8) {
+        uint4 w;
+        w.x = pack_bf16(o[i] * inv, o[i + 1] * inv);
+        w.y = pack_bf16(o[i + 2] * inv, o[i + 3] * inv);
+        w.z = pack_bf16(o[i + 4] * inv, o[i + 5] * inv);
+        w.w = pack_bf16(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(op + i) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// CUDA-core sibling: one block per (query, head, batch); scores staged in smem.  Comparator / bring-up only.
+__global__ void attn_enc_simt_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int D, float scale) {
+  extern __shared__ float sc[];  // S scores
+  __shared__ float qs[DH];
+  __shared__ float red[32];
+  const int q = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const bf16* base = qkv + (long long)b * S * 3 * D;
+  if (threadIdx.x < DH) qs[threadIdx.x] = __bfloat162float(base[(long long)q * 3 * D + h * DH + threadIdx.x]);
+  __syncthreads();
+  float lmax = -INFINITY;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    const bf16* kp = base + (long long)k * 3 * D + D + h * DH;
+    float a = 0.f;
+    for (int d = 0; d < DH; ++d) a = fmaf(qs[d], __bfloat162float(kp[d]), a);
+    a *= scale;
+    sc[k] = a;
+    lmax = fmaxf(lmax, a);
+  }
+  lmax = warp_max(lmax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lmax;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    const float e = expf(sc[k] - mx);
+    sc[k] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  if (threadIdx.x < DH) {
+    float a = 0.f;
+    for (int k = 0; k < S; ++k) a = fmaf(sc[k], __bfloat162float(base[(long long)k * 3 * D + 2 * D + h * DH + threadIdx.x]), a);
+    out[((long long)(b * S + q)) * D + h * DH + threadIdx.x] = __float2bfloat16(a / tot);
+  }
+}
+
+// V slice of qkv [B*S, 3D] -> vt [B, H, 64, Spad] (keys contiguous): the K-major B operand of the PV MMA.
+__global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vt, int S, int Spad, int H, int D) {
+  __shared__ bf16 tile[64][DH + 2];
+  const int s0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 64 * DH; i += blockDim.x) {
+    const int s = i / DH, d = i % DH;
+    tile[s][d] = (s0 + s < S) ? qkv[((long long)(b * S + s0 + s)) * 3 * D + 2 * D + h * DH + d] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * DH; i += blockDim.x) {
+    const int d = i / 64, s = i % 64;
+    if (s0 + s < Spad) vt[(((long long)b * H + h) * DH + d) * Spad + s0 + s] = tile[s][d];
+  }
+}
+
+}  // namespace
+
+int attn_enc_tc(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int B, int S, int Spad, int H) {
+  const int D = H * DH;
+  BW_CHECK(Spad % 8 == 0 && Spad >= S, "attn_enc: Spad=%d must be >= S and a multiple of 8", Spad);
+  CUtensorMap tmQK, tmVT;
+  if (int rc = make_tmap_2d_bf16(&tmQK, qkv, (uint64_t)B * S, (uint64_t)3 * D, (uint64_t)3 * D * 2, TQ, DH)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmVT, vt, (uint64_t)B * H * DH, (uint64_t)Spad, (uint64_t)Spad * 2, DH, 64)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BW_CUDA_OK(cudaFuncSetAttribute(attn_enc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.B = B; p.S = S; p.H = H; p.D = D;
+  p.scale_log2e = 0.125f * LOG2E;
+  p.out = out;
+  dim3 grid((S + TQ - 1) / TQ, H, B);
+  attn_enc_tc_kernel<<<grid, 192, ATT_SMEM, st>>>(tmQK, tmVT, p);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int attn_enc_simt(cudaStream_t st, const bf16* qkv, bf16* out, int B, int S, int H) {
+  const int D = H * DH;
+  dim3 grid(S, H, B);
+  attn_enc_simt_kernel<<<grid, 128, S * sizeof(float), st>>>(qkv, out, S, H, D, 0.125f);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int transpose_v(cudaStream_t st, const bf16* qkv, bf16* vt, int B, int S, int Spad, int H) {
+  dim3 grid((Spad + 63) / 64, H, B);
+  transpose_v_kernel<<<grid, 256, 0, st>>>(qkv, vt, S, Spad, H, H * DH);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bw

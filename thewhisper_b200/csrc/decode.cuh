@@ -1,0 +1,80 @@
+// Decoder-step kernels (q_len = 1, HBM-bound weight / KV streaming) and their argument blocks.
+#pragma once
+#include "common.cuh"
+
+namespace bw {
+
+// out[m, n] = epi( LN?(x[m, :]) . W[n, :] )   for m < M <= 8 rows per launch
+struct GemvArgs {
+  const float* x = nullptr;  // [M, K] fp32 rows (pitch ldx)
+  int ldx = 0;
+  const float* ln_g = nullptr;  // optional LayerNorm (eps 1e-5) applied to x rows first
+  const float* ln_b = nullptr;
+  const bf16* W = nullptr;  // [N, K]
+  int N = 0, K = 0, M = 0;
+  const float* bias = nullptr;
+  float alpha = 1.0f;
+  int alpha_cols = 0;  // alpha applies to columns [0, alpha_cols)
+  int act = 0;         // 1 = exact GELU
+  const float* residual = nullptr;  // [M, ldo] (may alias out)
+  float* out = nullptr;
+  int ldo = 0;
+  // optional self-KV scatter (fused QKV projection): columns [D,2D) -> kc, [2D,3D) -> vc at row (seq0+m, *pos)
+  bf16* kc = nullptr;
+  bf16* vc = nullptr;
+  int D = 0, Tmax = 0, seq0 = 0;
+  const int* pos = nullptr;
+};
+
+struct SelfAttnArgs {
+  const float* qkv = nullptr;  // [Q, 3D] fp32 (q already scaled)
+  const bf16* kc = nullptr;    // [Q, Tmax, D]
+  const bf16* vc = nullptr;
+  const int* anc = nullptr;    // [Q, Tmax] sequence slot holding position s for sequence q (null = own slot)
+  float* out = nullptr;        // [Q, D]
+  const int* pos = nullptr;
+  int H = 0, D = 0, Tmax = 0;
+};
+
+constexpr int XSPLIT = 8;    // key splits per (audio, head) in cross attention
+constexpr int MAXG = 8;      // max sequences (beams) sharing one audio's cross K/V
+
+struct CrossAttnArgs {
+  const float* q = nullptr;  // [Q, D] fp32 (scaled), Q = A*G
+  const bf16* kc = nullptr;  // [A, H, S, 64]
+  const bf16* vc = nullptr;  // [A, H, S, 64]
+  float* out = nullptr;      // [Q, D]
+  float* part_o = nullptr;   // [A, H, XSPLIT, G, 64]
+  float* part_ml = nullptr;  // [A, H, XSPLIT, G, 2]
+  unsigned* counters = nullptr;  // [A*H], zero between launches
+  int S = 0, H = 0, D = 0, G = 1;
+  // word timestamps: raw scores of alignment heads (beam 0 of each audio) -> align[(a*Ha + slot)*Tcap + step][S]
+  float* align = nullptr;
+  int align_slot = -1;  // slot of THIS layer's head `align_head`, resolved per launch via head_slots
+  const int* head_slots = nullptr;  // [H] slot per head for this layer or -1
+  int Ha = 0, Tcap = 0, step_base = 0;
+  const int* pos = nullptr;
+};
+
+struct SelectArgs {
+  const float* logits = nullptr;  // [Q, V]
+  int V = 0, Q = 0, Tmax = 0;
+  int* tokens = nullptr;       // [Q, Tmax]
+  int* finished = nullptr;     // [Q]
+  int* pos = nullptr;          // device scalar, advanced by the last block
+  unsigned* done_ctr = nullptr;
+  const unsigned* suppress_bits = nullptr;        // bitmap [ceil(V/32)]
+  const unsigned* begin_suppress_bits = nullptr;  // bitmap, applied when pos+1 == begin_index
+  int begin_index = 0;  // prompt length
+  int eos = 0, pad = 0;
+  int ts_rules = 0, ts_begin = 0, no_ts = 0, max_initial_ts = -1;
+  float* out_lse = nullptr;  // optional [Q]: log-sum-exp of the raw logits (parity / beam search)
+};
+
+int launch_gemv(cudaStream_t st, const GemvArgs& a);
+int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax);
+int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q);
+int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A);
+int launch_select(cudaStream_t st, const SelectArgs& a);
+
+}  // namespace bw
