@@ -1,0 +1,162 @@
+"""CPU tests of the host logic and of the oracle:
+  * oracle restatements (log-mel, logits rules, DTW, LCS) against the golden vectors minted from the real reference
+    and against the installed transformers implementations;
+  * the product's host side (window schedule, seam merge, generation control, ASRPipeline drop-in) run end to end on
+    a CPU stand-in engine (oracle/engine_stub.py) and compared with the real reference's pipeline outputs.
+No CUDA compute is called here."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLD
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle vs golden / transformers
+# ---------------------------------------------------------------------------------------------------------------------
+def test_mel_bank_and_logmel_restatement():
+    from oracle import hf_ref, whisper_ref
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.features import mel_filter_bank, num_valid_frames
+
+    gold = np.load(os.path.join(GOLD, "logmel.npz"))
+    bank = mel_filter_bank(128)
+    assert np.array_equal(bank, gold["mel_bank"])
+    assert abs(bank.astype(np.float64).sum() - gold["mel_bank_sum_nnz"][0]) < 1e-5 and (bank != 0).sum() == 394
+    # SURVEY.md §8c golden numbers (two-tone, 30 s)
+    st = gold["two_tone_30s_stats"]
+    assert abs(st[0] - (-0.374522)) < 2e-6 and abs(st[2] - 1.485354) < 2e-6
+    for secs in (10, 30):
+        m = whisper_ref.logmel_np(S.two_tone(secs), bank, secs * 16000)
+        assert np.abs(m[:, ::25] - gold[f"two_tone_{secs}s_sub"]).max() < 2e-4
+    x = (np.random.RandomState(0).randn(160000) * 0.1).astype(np.float32)
+    m = whisper_ref.logmel_np(x, bank, 160000)
+    assert np.abs(m[:, ::10] - gold["noise_10s_sub"]).max() < 2e-4
+    fe = S.make_feature_extractor(10)
+    assert np.abs(hf_ref.logmel(fe, x)[:, ::10] - gold["noise_10s_sub"]).max() == 0.0
+    assert num_valid_frames(int(7.3 * 16000), 160000) == int(gold["speech_7p3s_mask_sum"][0])
+
+
+def test_lcs_golden():
+    from oracle import hf_ref
+    from thewhisper_b200.hostproc import merge_overlapping
+
+    cases = json.load(open(os.path.join(GOLD, "lcs_cases.json")))
+    assert len(cases) == 40
+    for c in cases:
+        if "ts" in c:
+            ts = [[tuple(t) for t in s] for s in c["ts"]]
+            for fn in (hf_ref.lcs_merge, merge_overlapping):
+                a, b = fn(c["seqs"], ts)
+                assert a == c["out"] and [list(t) for t in b] == c["out_ts"]
+        else:
+            for fn in (hf_ref.lcs_merge, merge_overlapping):
+                assert fn(c["seqs"]) == c["out"]
+
+
+def test_logits_rules_match_transformers():
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+
+    from oracle import whisper_ref
+    from thewhisper_b200 import synthetic as S
+
+    g = S.make_generation_config("tiny-test")
+    rng = np.random.RandomState(0)
+    begin = 3
+    procs = [SuppressTokensAtBeginLogitsProcessor(g.begin_suppress_tokens, begin_index=begin),
+             SuppressTokensLogitsProcessor(g.suppress_tokens), WhisperTimeStampLogitsProcessor(g, begin_index=begin)]
+    tb = S.TIMESTAMP_BEGIN
+    histories = [[], [tb + 3], [tb + 3, 400], [tb + 3, 400, tb + 9], [tb + 3, 400, tb + 9, tb + 9], [tb, 300, 301],
+                 [tb + 1, 5, tb + 7, tb + 7, 9], [tb + 2, tb + 2]]
+    for h in histories:
+        for trial in range(3):
+            seq = [S.SOT, S.LANG_EN, S.TRANSCRIBE] + h
+            scores = (rng.randn(S.VOCAB) * 2).astype(np.float32)
+            if trial == 1:
+                scores[tb:] += 4.0  # make the "sum of timestamp probability" rule fire
+            ref = torch.from_numpy(scores)[None].clone()
+            ids = torch.tensor([seq])
+            for p in procs:
+                ref = p(ids, ref)
+            mine = whisper_ref.process_logits(scores, seq, begin, suppress=g.suppress_tokens, begin_suppress=g.begin_suppress_tokens,
+                                              ts_rules=True, ts_begin=tb, no_ts=S.NOTIMESTAMPS, eos=S.EOS, max_initial_ts=50)
+            assert np.array_equal(np.isinf(mine), np.isinf(ref[0].numpy())), h
+            assert int(np.argmax(mine)) == int(ref[0].argmax())
+
+
+def test_dtw_and_median_match_transformers():
+    from transformers.models.whisper.generation_whisper import _dynamic_time_warping, _median_filter
+
+    from oracle import whisper_ref
+
+    rng = np.random.RandomState(3)
+    for T, N in ((1, 5), (7, 40), (30, 250)):
+        m = rng.randn(T, N)
+        a = whisper_ref.dtw(m)
+        b = _dynamic_time_warping(m)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    x = rng.randn(2, 3, 9, 50).astype(np.float32)
+    assert np.array_equal(whisper_ref.median_filter(x, 7), _median_filter(torch.from_numpy(x), 7).numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# product host logic on the CPU stand-in engine vs the real reference's pipeline outputs
+# ---------------------------------------------------------------------------------------------------------------------
+def _stub_pipeline(monkeypatch, preset, gain, chunk_s, batch_size):
+    from oracle.engine_stub import StubEngine
+    from thewhisper_b200 import synthetic as S
+    import thewhisper_b200.nvidia.asr_pipeline as ap
+
+    model = S.make_hf_model(preset, seed=0, layer_gain=gain)
+
+    def factory(state_dict, dims, chunk_length_s=30, device=None, max_audios=1, max_beams=1, alignment_heads=None, weights=None, **kw):
+        return StubEngine(model, chunk_length_s=chunk_length_s, max_audios=max_audios, max_beams=max_beams,
+                          alignment_heads=alignment_heads)
+
+    monkeypatch.setattr(ap, "WhisperEngine", factory)
+    return ap.ASRPipeline(model, feature_extractor=S.make_feature_extractor(chunk_s), tokenizer=S.make_tokenizer(),
+                          chunk_length_s=chunk_s, device="cuda", batch_size=batch_size)
+
+
+def _same(a, b, tol=1e-6):
+    if isinstance(a, dict):
+        return set(a) == set(b) and all(_same(a[k], b[k], tol) for k in a)
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_same(x, y, tol) for x, y in zip(a, b))
+    if isinstance(a, float) or isinstance(b, float):
+        return a is not None and b is not None and abs(a - b) <= tol
+    return a == b
+
+
+@pytest.mark.parametrize("mode", ["plain", "ts", "word"])
+def test_pipeline_host_logic_matches_reference(monkeypatch, mode):
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, "model_tiny10.json")))
+    pipe = _stub_pipeline(monkeypatch, meta["preset"], meta["layer_gain"], meta["chunk_s"], batch_size=4)
+    audio = S.synth_audio(meta["audio_s"], seed=2000)
+    gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": 32}
+    kw = {"plain": {}, "ts": {"return_timestamps": True}, "word": {"return_timestamps": "word"}}[mode]
+    out = pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=4, generate_kwargs=dict(gk), **kw)
+    ref = meta["pipeline"][mode]
+    norm = json.loads(json.dumps(out, default=lambda o: float(o)))
+    assert _same(norm, ref), (norm, ref)
+
+
+def test_window_schedule_matches_transformers():
+    from transformers.pipelines.automatic_speech_recognition import chunk_iter
+
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.hostproc import chunk_windows
+
+    fe = S.make_feature_extractor(10)
+    for n, cl, sl, sr in ((400000, 144000, 24000, 24000), (144000, 144000, 24000, 24000), (150000, 144000, 24000, 24000),
+                          (100, 144000, 24000, 24000), (500000, 160000, 0, 30000)):
+        x = np.zeros(n, dtype=np.float32)
+        ref = [(it["stride"], it["is_last"]) for it in chunk_iter(x, fe, cl, sl, sr)]
+        mine = [(stride, last) for _, _, stride, last in chunk_windows(n, cl, sl, sr)]
+        assert mine == ref, (n, mine, ref)
