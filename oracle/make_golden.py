@@ -178,6 +178,82 @@ def golden_model(ASRPipeline, preset, tag, chunk_s, audio_s, n_tf=24, max_new=32
     print(f"model_{tag}: {time.time() - t0:.1f}s greedy={out['greedy_tokens'][:12]}")
 
 
+STREAM_VOCAB = ["The", "quick,", "brown", "fox.", "It", "jumps", "over;", "lazy", "dogs!", "gonNA", ".", "-run", "and", "then",
+                "stops?", "we", "wanNA", "go", "now:", "ok"]
+
+
+class FakeWordBackend:
+    """Deterministic stand-in for the ASR backend: one word per 0.4 s of absolute time, so re-transcriptions of a
+    growing buffer agree with each other; used to pin the streaming state machine independently of any model."""
+
+    def __init__(self):
+        self.calls = []
+
+    def transcribe(self, audio, buffer_start_time, sample_rate):
+        dur = len(audio) / sample_rate
+        self.calls.append(round(dur, 4))
+        words = []
+        k = int(np.ceil(buffer_start_time / 0.4 - 1e-9))
+        while k * 0.4 + 0.3 <= buffer_start_time + dur:
+            if k % 13 != 7:  # a pause now and then
+                words.append({"text": (" " if k % 5 else "") + STREAM_VOCAB[k % len(STREAM_VOCAB)], "start": round(k * 0.4, 4),
+                              "end": round(k * 0.4 + 0.3, 4)})
+            k += 1
+        return words
+
+
+class FakeVad:
+    def __call__(self, chunk, sr):
+        return torch.tensor(1.0 if float(chunk.abs().mean()) > 0.01 else 0.0)
+
+    def reset_states(self):
+        pass
+
+
+def stream_audio(seconds=40.0):
+    x = S.synth_audio(seconds, seed=77, kind="noise")
+    t = np.arange(len(x)) / 16000.0
+    x[(t % 9.0) > 6.5] = 0.0  # 2.5 s of silence every 9 s
+    return x
+
+
+def golden_streaming():
+    import importlib.machinery
+    import types
+
+    for name, attrs in (("sounddevice", ["InputStream"]), ("librosa", ["load", "resample"])):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            for a in attrs:
+                setattr(m, a, None)
+            sys.modules[name] = m
+    from thestage_speechkit.streaming.streaming_pipeline import StreamingPipeline as RefStreaming
+
+    out = {}
+    audio = stream_audio()
+    for tag, use_vad, step_s in (("novad_0p5", False, 0.5), ("novad_0p05", False, 0.05), ("vad_0p05", True, 0.05)):
+        be = FakeWordBackend()
+        if use_vad:
+            orig = torch.hub.load
+            torch.hub.load = lambda *a, **k: (FakeVad(), None)
+        try:
+            sp = RefStreaming(backend=be, use_vad=use_vad, chunk_length_s=15, min_process_chunk_s=0.5)
+        finally:
+            if use_vad:
+                torch.hub.load = orig
+        n = int(step_s * 16000)
+        events = []
+        for i in range(0, len(audio), n):
+            c, u = sp(audio[i:i + n])
+            if c or u:
+                events.append([i // n, _jsonable(c), _jsonable(u)])
+        out[tag] = {"step_s": step_s, "use_vad": use_vad, "backend_calls": be.calls, "events": events}
+        print("streaming", tag, "calls", len(be.calls), "events", len(events), "max buffer", max(be.calls))
+    with open(os.path.join(GOLD, "streaming.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--large", action="store_true", help="also mint the large-v3-dims goldens (minutes)")
@@ -190,6 +266,8 @@ def main():
         golden_mel()
     if a.only in ("", "lcs"):
         golden_lcs(ref_lcs)
+    if a.only in ("", "stream"):
+        golden_streaming()
     if a.only in ("", "tiny"):
         golden_model(ASRPipeline, "tiny-test", "tiny10", chunk_s=10, audio_s=25.0, gain=8.0)
         golden_model(ASRPipeline, "small-test", "small30", chunk_s=30, audio_s=70.0, gain=8.0)
