@@ -94,6 +94,12 @@ int bw_decode_read(bw_engine* e, int32_t* tokens_host, int32_t* finished_host, i
 /* beam search support: reorder sequences (new sequence i continues old sequence parent[i]) by permuting the
  * per-token block table; overwrite the token just selected.  Host arrays of A*G entries. */
 int bw_decode_reorder(bw_engine* e, const int32_t* parent_host, const int32_t* next_token_host, void* stream);
+/* beam search step: upload the running scores [A*G], run one decoder step, download each sequence's 2*G best
+ * continuations (score = running score + processed log-prob, token id; -inf / -1 when fewer exist).
+ * Replaces the log_softmax + processors + topk part of TF/generation/utils.py:3254-3275; the beam bookkeeping
+ * (:2945-3072) stays on the host (thewhisper_b200/beam.py). */
+int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_scores_host, int32_t* cand_tokens_host,
+                        void* stream);
 /* word timestamps for audio a: n_tokens generated tokens starting at alignment row 0, num_frames valid encoder
  * frames (<= S); out_host [n_tokens + 1] seconds */
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision,

@@ -76,7 +76,8 @@ struct bw_engine {
   unsigned *done_ctr = nullptr, *xcounters = nullptr, *sup_bits = nullptr, *bsup_bits = nullptr;
   float *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dq = nullptr, *dh = nullptr, *logits = nullptr, *part_o = nullptr,
         *part_ml = nullptr, *align = nullptr, *lse = nullptr, *ts_work = nullptr, *ts_out = nullptr;
-  int *reorder_tmp = nullptr;
+  int *reorder_tmp = nullptr, *cand_tokens = nullptr;
+  float *run_scores = nullptr, *cand_scores = nullptr;
   size_t align_bytes = 0;
   // current decode session
   int A = 0, G = 1, Q = 0;
@@ -287,6 +288,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
   s.begin_index = e->opts.begin_index; s.eos = e->opts.eos_token; s.pad = e->opts.pad_token;
   s.ts_rules = e->opts.timestamp_rules; s.ts_begin = e->opts.timestamp_begin; s.no_ts = e->opts.no_timestamps_token;
   s.max_initial_ts = e->opts.max_initial_timestamp_index; s.out_lse = e->lse;
+  if (G > 1) { s.n_cand = 2 * G; s.run_scores = e->run_scores; s.cand_scores = e->cand_scores; s.cand_tokens = e->cand_tokens; }
   return launch_select(st, s);
 }
 
@@ -348,7 +350,7 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
   BW_CHECK(cfg->d_model % 64 == 0 && cfg->ffn % 64 == 0, "d_model and ffn must be multiples of 64");
   BW_CHECK(cfg->n_mels == 128 || cfg->n_mels == 64, "n_mels=%d unsupported (the conv stem's TMA view needs a multiple of 64)", cfg->n_mels);
   BW_CHECK(cfg->max_beams >= 1 && cfg->max_beams <= MAXG, "max_beams must be in 1..%d", MAXG);
-  BW_CHECK(cfg->max_source_positions >= 1 && cfg->max_source_positions <= 2048, "max_source_positions out of range");
+  BW_CHECK(cfg->max_source_positions >= 1 && cfg->max_source_positions <= 1536, "max_source_positions out of range (1..1536)");
   BW_CHECK(bw_device_count() > 0, "no CUDA device: thewhisper_b200 has no CPU fallback");
   bw_engine* e = new bw_engine();
   e->cfg = *cfg;
@@ -455,6 +457,9 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "dh", &e->dh, (size_t)Qm * c.ffn)) return -1;
   if (dalloc(e, "logits", &e->logits, (size_t)Qm * V)) return -1;
   if (dalloc(e, "lse", &e->lse, (size_t)Qm)) return -1;
+  if (dalloc(e, "run_scores", &e->run_scores, (size_t)Qm)) return -1;
+  if (dalloc(e, "cand_scores", &e->cand_scores, (size_t)Qm * 16)) return -1;
+  if (dalloc(e, "cand_tokens", &e->cand_tokens, (size_t)Qm * 16)) return -1;
   if (dalloc(e, "part_o", &e->part_o, (size_t)A * H * XSPLIT * c.max_beams * 64)) return -1;
   if (dalloc(e, "part_ml", &e->part_ml, (size_t)A * H * XSPLIT * c.max_beams * 2)) return -1;
   if (dalloc(e, "head_slots", &e->head_slots, (size_t)c.dec_layers * H)) return -1;
@@ -600,6 +605,19 @@ int bw_decode_reorder(bw_engine* e, const int32_t* parent_host, const int32_t* n
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaMemcpyAsync(e->anc, e->anc_tmp, sizeof(int) * Q * Tmax, cudaMemcpyDeviceToDevice, st));
   BW_CUDA_OK(cudaMemcpyAsync(e->tokens, e->reorder_tmp, sizeof(int) * Q * Tmax, cudaMemcpyDeviceToDevice, st));
+  BW_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_scores_host, int32_t* cand_tokens_host, void* stream) {
+  BW_CHECK(e && e->finalized && e->Q > 0 && e->G > 1, "bw_decode_beam_step: no beam decode in progress");
+  BW_CHECK(run_scores_host && cand_scores_host && cand_tokens_host, "bw_decode_beam_step: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Q = e->Q, nc = 2 * e->G;
+  BW_CUDA_OK(cudaMemcpyAsync(e->run_scores, run_scores_host, sizeof(float) * Q, cudaMemcpyHostToDevice, st));
+  if (int rc = bw_decode_run(e, 1, stream)) return rc;
+  BW_CUDA_OK(cudaMemcpyAsync(cand_scores_host, e->cand_scores, sizeof(float) * Q * nc, cudaMemcpyDeviceToHost, st));
+  BW_CUDA_OK(cudaMemcpyAsync(cand_tokens_host, e->cand_tokens, sizeof(int) * Q * nc, cudaMemcpyDeviceToHost, st));
   BW_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -64,9 +64,12 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 // 16-byte streaming load that does not pollute L1 (weights / KV are read once per step)
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;
+  // volatile + "memory": the compiler must not sink these below later smem traffic / barriers -- the decode kernels
+  // rely on all of a CTA's loads being issued up front (one DRAM round trip)
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+               : "l"(p)
+               : "memory");
   return r;
 }
 

@@ -36,7 +36,7 @@ struct SelfAttnArgs {
   int H = 0, D = 0, Tmax = 0;
 };
 
-constexpr int XSPLIT = 8;    // key splits per (audio, head) in cross attention
+constexpr int XSPLIT = 12;   // key splits per (audio, head) in cross attention (<= 128 keys each: S <= 1536)
 constexpr int MAXG = 8;      // max sequences (beams) sharing one audio's cross K/V
 
 struct CrossAttnArgs {
@@ -69,6 +69,11 @@ struct SelectArgs {
   int eos = 0, pad = 0;
   int ts_rules = 0, ts_begin = 0, no_ts = 0, max_initial_ts = -1;
   float* out_lse = nullptr;  // optional [Q]: log-sum-exp of the raw logits (parity / beam search)
+  // beam search: per sequence the n_cand (<= 16) best continuations, running score included
+  int n_cand = 0;
+  const float* run_scores = nullptr;  // [Q]
+  float* cand_scores = nullptr;       // [Q, n_cand]
+  int* cand_tokens = nullptr;         // [Q, n_cand]
 };
 
 int launch_gemv(cudaStream_t st, const GemvArgs& a);

@@ -1,0 +1,510 @@
+// The HBM-streaming kernels of a decoder step (q_len = 1): GEMV with fused LayerNorm / epilogues, causal self-attention
+// over the token KV cache, cross-attention over the resident encoder K/V.
+//
+// At batch 1 every one of these moves only 3-13 MB, i.e. ~20-90 KB per SM: they are bound by DRAM *latency*, not
+// bandwidth, unless every byte a CTA needs is requested up front.  So each kernel issues ALL of its 16-byte weight / KV
+// loads into registers first (one DRAM round trip), overlaps the x staging + LayerNorm prologue with them, and only
+// then computes.  (First version looped load->use with 4-8 loads in flight: 3.0 ms per step, 10% of the HBM roofline;
+// see profiles/.)
+#include <math.h>
+
+#include "decode.cuh"
+#include "kernels.h"
+
+namespace bw {
+
+namespace {
+
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_WARPS = GEMV_THREADS / 32;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// 16-byte async copy global -> shared (LDGSTS): issued up front at no register cost; ptxas cannot sink it the way it
+// sinks ld.global.nc, which is what serialised the K and V fetches of the attention kernels into two DRAM round trips
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NC, int R>
+struct WRegs {
+  uint4 w[R][NC];
+};
+
+// lane l holds elements [l*8 + i*256, +8) of each row, i < NC  (512 contiguous bytes per warp-load: fully coalesced)
+template <int NC, int R>
+__device__ __forceinline__ void load_rows(WRegs<NC, R>& wr, const bf16* __restrict__ W, int K, int n, int n_end, int lane) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = min(n + r, n_end - 1);  // clamp: a duplicate row whose result is discarded
+    const bf16* wp = W + (long long)row * K;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane * 8 + i * 256;
+      wr.w[r][i] = (k < K) ? ld_nc_u4(wp + k) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[m, n] = epi( LN?(x[m, :]) . W[n, :] ), m < MB <= 8.  NC = ceil(K / 256) bound, R rows per warp in flight.
+// ------------------------------------------------------------------------------------------------
+template <int MB, int NC, int R, bool PIPE>
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvArgs a, const int rows_per_warp) {
+  extern __shared__ float xs[];  // [MB][K]
+  __shared__ float red[GEMV_WARPS][MB];
+  __shared__ float stat[2][MB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int gw = blockIdx.x * GEMV_WARPS + warp;
+  const int n_begin = gw * rows_per_warp;
+  const int n_end = min(a.N, n_begin + rows_per_warp);
+
+  // 1) weight rows of the first pass: requested before anything else so the DRAM latency hides the prologue
+  WRegs<NC, R> cur;
+  if (n_begin < n_end) load_rows<NC, R>(cur, a.W, K, n_begin, n_end, lane);
+
+  // 2) stage x (and LayerNorm it): two-pass, biased variance, eps 1e-5 like torch.nn.LayerNorm
+  for (int i = threadIdx.x; i < MB * K; i += GEMV_THREADS) {
+    const int m = i / K, k = i - m * K;
+    xs[i] = (m < a.M) ? a.x[(long long)m * a.ldx + k] : 0.f;
+  }
+  __syncthreads();
+  if (a.ln_g) {
+    float part[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) part[m] = 0.f;
+    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+#pragma unroll
+      for (int m = 0; m < MB; ++m) part[m] += xs[m * K + k];
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const float s = warp_sum(part[m]);
+      if (lane == 0) red[warp][m] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < MB) {
+      float s = 0.f;
+      for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
+      stat[0][threadIdx.x] = s / (float)K;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MB; ++m) part[m] = 0.f;
+    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const float d = xs[m * K + k] - stat[0][m];
+        part[m] = fmaf(d, d, part[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const float s = warp_sum(part[m]);
+      if (lane == 0) red[warp][m] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < MB) {
+      float s = 0.f;
+      for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
+      stat[1][threadIdx.x] = rsqrtf(s / (float)K + 1e-5f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+      const float g = a.ln_g[k], bb = a.ln_b[k];
+#pragma unroll
+      for (int m = 0; m < MB; ++m) xs[m * K + k] = (xs[m * K + k] - stat[0][m]) * stat[1][m] * g + bb;
+    }
+    __syncthreads();
+  }
+
+  const int pos = a.pos ? *a.pos : 0;
+  for (int n = n_begin; n < n_end; n += R) {
+    WRegs<NC, R> nxt;
+    const bool has_next = (n + R) < n_end;
+    if (PIPE && has_next) load_rows<NC, R>(nxt, a.W, K, n + R, n_end, lane);
+    float acc[R][MB];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane * 8 + i * 256;
+      if (k < K) {
+        float wf[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r) unpack8(cur.w[r][i], wf[r]);
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          const float4 xa = *reinterpret_cast<const float4*>(&xs[m * K + k]);
+          const float4 xb = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float s = acc[r][m];
+            s = fmaf(wf[r][0], xa.x, s); s = fmaf(wf[r][1], xa.y, s); s = fmaf(wf[r][2], xa.z, s); s = fmaf(wf[r][3], xa.w, s);
+            s = fmaf(wf[r][4], xb.x, s); s = fmaf(wf[r][5], xb.y, s); s = fmaf(wf[r][6], xb.z, s); s = fmaf(wf[r][7], xb.w, s);
+            acc[r][m] = s;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int m = 0; m < MB; ++m) acc[r][m] = warp_sum(acc[r][m]);
+    // lanes [16r, 16r + MB) finish row n + r
+    const int m = lane & 15, r_sel = lane >> 4;
+    const int nn = n + r_sel;
+    if (r_sel < R && m < MB && m < a.M && nn < n_end) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int mm = 0; mm < MB; ++mm)
+          if (r == r_sel && mm == m) v = acc[r][mm];
+      if (a.bias) v += a.bias[nn];
+      if (nn < a.alpha_cols) v *= a.alpha;
+      if (a.act == 1) v = gelu_erf(v);
+      if (a.residual) v += a.residual[(long long)m * a.ldo + nn];
+      a.out[(long long)m * a.ldo + nn] = v;
+      if (a.kc && nn >= a.D) {
+        const long long row = ((long long)(a.seq0 + m) * a.Tmax + pos) * a.D;
+        if (nn < 2 * a.D) a.kc[row + nn - a.D] = __float2bfloat16(v);
+        else a.vc[row + nn - 2 * a.D] = __float2bfloat16(v);
+      }
+    }
+    if (PIPE) {
+      if (has_next) cur = nxt;
+    } else if (has_next) {
+      load_rows<NC, R>(cur, a.W, K, n + R, n_end, lane);
+    }
+  }
+}
+
+__device__ __forceinline__ float block_max4(float v, float* red4) {  // 128 threads
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float r = fmaxf(fmaxf(red4[0], red4[1]), fmaxf(red4[2], red4[3]));
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum4(float v, float* red4) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float r = red4[0] + red4[1] + red4[2] + red4[3];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// causal self-attention over cached positions 0..pos of one (sequence, head).  128 threads = 16 key groups x 8 lanes;
+// a lane owns 8 of the 64 head dims, so one warp-load covers 4 whole 128-byte K (or V) rows.  Keys are walked in
+// chunks of 128 with all 8 loads of a chunk in flight.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
+  extern __shared__ __align__(16) uint8_t dyn[];  // K rows [Tmax][128 B] | V rows [Tmax][128 B] | scores [Tmax]
+  __shared__ float red4[4];
+  __shared__ float redo[16][64];
+  const int h = blockIdx.x, q = blockIdx.y;
+  const int pos = *a.pos;
+  const int n = pos + 1;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  uint8_t* sK = dyn;
+  uint8_t* sV = dyn + (size_t)a.Tmax * 128;
+  float* sc = reinterpret_cast<float*>(dyn + (size_t)a.Tmax * 256);
+  // every K and V row of this (sequence, head) is requested now: one DRAM round trip for the whole kernel
+  for (int s = grp; s < n; s += 16) {
+    const int slot = a.anc ? a.anc[q * a.Tmax + s] : q;
+    const long long off = ((long long)slot * a.Tmax + s) * a.D + h * 64 + sub * 8;
+    cp_async16(sK + s * 128 + sub * 16, a.kc + off);
+    cp_async16(sV + s * 128 + sub * 16, a.vc + off);
+  }
+  const float* qp = a.qkv + (long long)q * 3 * a.D + h * 64 + sub * 8;
+  float qv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qv[i] = qp[i];
+  cp_async_wait_all();  // each thread reads back only what it copied itself
+  float lmax = -INFINITY;
+  for (int sb = 0; sb < n; sb += 16) {  // uniform trip count: the shuffles need all 32 lanes
+    const int s = sb + grp;
+    float d = 0.f;
+    if (s < n) {
+      float kf[8];
+      unpack8(*reinterpret_cast<const uint4*>(sK + s * 128 + sub * 16), kf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d = fmaf(qv[j], kf[j], d);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (s < n) {
+      if (sub == 0) sc[s] = d;
+      lmax = fmaxf(lmax, d);
+    }
+  }
+  const float mx = block_max4(lmax, red4);  // (also orders the sc[] writes before the reads below)
+  float lsum = 0.f;
+  for (int s = threadIdx.x; s < n; s += 128) {
+    const float e = __expf(sc[s] - mx);
+    sc[s] = e;
+    lsum += e;
+  }
+  const float inv = 1.0f / block_sum4(lsum, red4);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int s = grp; s < n; s += 16) {
+    float vf[8];
+    unpack8(*reinterpret_cast<const uint4*>(sV + s * 128 + sub * 16), vf);
+    const float p = sc[s];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) redo[grp][sub * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) o += redo[g][threadIdx.x];
+    a.out[(long long)q * a.D + h * 64 + threadIdx.x] = o * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-attention over the encoder K/V of one audio, shared by its G beams.  XSPLIT key splits per (audio, head), at most
+// 128 keys per split, so a CTA's whole K and V slice (2 x 16 KB) is requested up front: 16 x 16-byte loads per thread,
+// one DRAM round trip.  The last-arriving split block merges the partials (flash-decoding), no extra launch.
+// ------------------------------------------------------------------------------------------------
+constexpr int XK = 128;
+
+template <int GM>  // compile-time bound on the beams per audio (1 or MAXG)
+__global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) {
+  __shared__ float sc[GM][XK];
+  __shared__ float redo[16][GM][64];
+  __shared__ float red4[4];
+  __shared__ float gm[GM], gl[GM];
+  __shared__ unsigned is_last;
+  const int split = blockIdx.x, h = blockIdx.y, au = blockIdx.z;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int G = (GM == 1) ? 1 : a.G;
+  const int ks = (a.S + XSPLIT - 1) / XSPLIT;
+  const int s0 = split * ks;
+  const int n = max(0, min(a.S, s0 + ks) - s0);
+  const bf16* kbase = a.kc + (((long long)au * a.H + h) * a.S + s0) * 64 + sub * 8;
+  const bf16* vbase = a.vc + (((long long)au * a.H + h) * a.S + s0) * 64 + sub * 8;
+
+  extern __shared__ __align__(16) uint8_t dyn[];  // K slice [XK][128 B] | V slice [XK][128 B]
+  uint8_t* sK = dyn;
+  uint8_t* sV = dyn + XK * 128;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = i * 16 + grp;
+    if (kk < n) {
+      cp_async16(sK + kk * 128 + sub * 16, kbase + (long long)kk * 64);
+      cp_async16(sV + kk * 128 + sub * 16, vbase + (long long)kk * 64);
+    }
+  }
+  float qv[GM][8];
+#pragma unroll
+  for (int g = 0; g < GM; ++g) {
+    if (g < G) {
+      const float* qp = a.q + (long long)(au * G + g) * a.D + h * 64 + sub * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qv[g][j] = qp[j];
+    }
+  }
+  const int slot = a.head_slots ? a.head_slots[h] : -1;
+  float* align_row = nullptr;
+  if (slot >= 0 && a.align) {
+    const int step = *a.pos - a.step_base;
+    if (step >= 0 && step < a.Tcap) align_row = a.align + (((long long)au * a.Ha + slot) * a.Tcap + step) * a.S + s0;
+  }
+  cp_async_wait_all();  // each thread reads back only the 16-byte pieces it copied itself
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = i * 16 + grp;
+    float kf[8];
+    if (kk < n) unpack8(*reinterpret_cast<const uint4*>(sK + kk * 128 + sub * 16), kf);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kf[j] = 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < GM; ++g) {
+      if (g < G) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d = fmaf(qv[g][j], kf[j], d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (sub == 0 && kk < n) {
+          sc[g][kk] = d;
+          if (g == 0 && align_row) align_row[kk] = d;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int g = 0; g < G; ++g) {  // n <= 128: one key per thread
+    const float v = (threadIdx.x < n) ? sc[g][threadIdx.x] : -INFINITY;
+    const float mx = block_max4(v, red4);
+    const float e = (threadIdx.x < n) ? __expf(v - mx) : 0.f;
+    if (threadIdx.x < n) sc[g][threadIdx.x] = e;
+    const float sum = block_sum4(e, red4);
+    if (threadIdx.x == 0) {
+      gm[g] = mx;
+      gl[g] = sum;
+    }
+  }
+  __syncthreads();
+  float acc[GM][8];
+#pragma unroll
+  for (int g = 0; g < GM; ++g)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = i * 16 + grp;
+    if (kk < n) {
+      float vf[8];
+      unpack8(*reinterpret_cast<const uint4*>(sV + kk * 128 + sub * 16), vf);
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        if (g < G) {
+          const float p = sc[g][kk];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[g][j] = fmaf(p, vf[j], acc[g][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < GM; ++g)
+    if (g < G) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) redo[grp][g][sub * 8 + j] = acc[g][j];
+    }
+  __syncthreads();
+  const long long pbase = (((long long)au * a.H + h) * XSPLIT + split) * G;
+  if (threadIdx.x < 64) {
+    for (int g = 0; g < G; ++g) {
+      float o = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) o += redo[r][g][threadIdx.x];
+      a.part_o[(pbase + g) * 64 + threadIdx.x] = o;
+    }
+  }
+  if (threadIdx.x < G) {
+    a.part_ml[(pbase + threadIdx.x) * 2 + 0] = gm[threadIdx.x];
+    a.part_ml[(pbase + threadIdx.x) * 2 + 1] = gl[threadIdx.x];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&a.counters[au * a.H + h], 1u);
+    is_last = (prev == XSPLIT - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 64) {
+    const int d = threadIdx.x;
+    const long long hb = ((long long)au * a.H + h) * XSPLIT * G;
+    for (int g = 0; g < G; ++g) {
+      float M = -INFINITY;
+      for (int sp = 0; sp < XSPLIT; ++sp) {
+        const float l = __ldcg(&a.part_ml[(hb + (long long)sp * G + g) * 2 + 1]);
+        if (l > 0.f) M = fmaxf(M, __ldcg(&a.part_ml[(hb + (long long)sp * G + g) * 2 + 0]));
+      }
+      float L = 0.f, o = 0.f;
+      for (int sp = 0; sp < XSPLIT; ++sp) {
+        const float l = __ldcg(&a.part_ml[(hb + (long long)sp * G + g) * 2 + 1]);
+        if (l > 0.f) {
+          const float w = __expf(__ldcg(&a.part_ml[(hb + (long long)sp * G + g) * 2 + 0]) - M);
+          L = fmaf(l, w, L);
+          o = fmaf(__ldcg(&a.part_o[(hb + (long long)sp * G + g) * 64 + d]), w, o);
+        }
+      }
+      a.out[(long long)(au * G + g) * a.D + h * 64 + d] = o / L;
+    }
+  }
+  if (threadIdx.x == 0) a.counters[au * a.H + h] = 0u;
+}
+
+template <int MB, int NC, int R, bool PIPE>
+int launch_gemv_t(cudaStream_t st, const GemvArgs& a, int grid, int rpw, size_t smem) {
+  static bool attr = false;
+  if (!attr) {
+    BW_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<MB, NC, R, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  gemv_kernel<MB, NC, R, PIPE><<<grid, GEMV_THREADS, smem, st>>>(a, rpw);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int MB>
+int launch_gemv_mb(cudaStream_t st, const GemvArgs& a) {
+  const size_t smem = (size_t)MB * a.K * sizeof(float);
+  if (a.K <= 1280) {
+    // two rows per warp in flight; ~2 CTAs per SM for small N, software-pipelined row pairs for the LM head
+    int rpw = (a.N + 296 * GEMV_WARPS - 1) / (296 * GEMV_WARPS);
+    rpw = (rpw + 1) & ~1;
+    if (rpw < 2) rpw = 2;
+    const int grid = (a.N + rpw * GEMV_WARPS - 1) / (rpw * GEMV_WARPS);
+    return launch_gemv_t<MB, 5, 2, true>(st, a, grid, rpw, smem);
+  }
+  // long rows (fc2, K = 4*D): one row per warp, all 20 loads of the row in flight
+  int rpw = (a.N + 592 * GEMV_WARPS - 1) / (592 * GEMV_WARPS);
+  if (rpw < 1) rpw = 1;
+  const int grid = (a.N + rpw * GEMV_WARPS - 1) / (rpw * GEMV_WARPS);
+  return launch_gemv_t<MB, 20, 1, false>(st, a, grid, rpw, smem);
+}
+
+}  // namespace
+
+int launch_gemv(cudaStream_t st, const GemvArgs& a) {
+  BW_CHECK(a.M >= 1 && a.M <= 8, "gemv: M=%d must be in 1..8", a.M);
+  BW_CHECK(a.K % 8 == 0 && a.K <= 5120, "gemv: K=%d must be a multiple of 8 and <= 5120", a.K);
+  if (a.M <= 1) return launch_gemv_mb<1>(st, a);
+  if (a.M <= 2) return launch_gemv_mb<2>(st, a);
+  if (a.M <= 4) return launch_gemv_mb<4>(st, a);
+  return launch_gemv_mb<8>(st, a);
+}
+
+int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q) {
+  const size_t smem = (size_t)a.Tmax * (256 + sizeof(float));
+  static bool attr = false;
+  if (!attr) {
+    BW_CUDA_OK(cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  BW_CHECK(smem <= 200 * 1024, "self_attn: Tmax=%d too large", a.Tmax);
+  self_attn_kernel<<<dim3(a.H, Q), 128, smem, st>>>(a);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A) {
+  BW_CHECK(a.G >= 1 && a.G <= MAXG, "cross_attn: G=%d must be in 1..%d", a.G, MAXG);
+  BW_CHECK(a.S <= XSPLIT * XK, "cross_attn: S=%d exceeds %d", a.S, XSPLIT * XK);
+  if (a.G == 1) cross_attn_kernel<1><<<dim3(XSPLIT, a.H, A), 128, 2 * XK * 128, st>>>(a);
+  else cross_attn_kernel<MAXG><<<dim3(XSPLIT, a.H, A), 128, 2 * XK * 128, st>>>(a);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bw
