@@ -59,9 +59,40 @@ class StubEngine:
         self._prompts = np.asarray(prompts)
         self._opts = opts
         self._A = A
+        self._G = G
+        self._plen = self._prompts.shape[1]
+        self._seqs = [list(map(int, r)) for r in self._prompts]
+
+    @torch.no_grad()
+    def decode_beam_step(self, run_scores):
+        """full re-forward of every sequence (no cache: test sizes only); log-softmax, rules, per-sequence top 2G"""
+        A, G, o = self._A, self._G, self._opts
+        ids = torch.tensor(self._seqs, dtype=torch.long)
+        enc = self.enc[:A].repeat_interleave(G, dim=0)
+        out = self.model.model.decoder(input_ids=ids, encoder_hidden_states=enc)
+        lg = self.model.proj_out(out.last_hidden_state[:, -1]).float()
+        lp = torch.log_softmax(lg, dim=-1).numpy()
+        K = 2 * G
+        cs = np.full((A * G, K), -np.inf, dtype=np.float32)
+        ct = np.full((A * G, K), -1, dtype=np.int32)
+        for q in range(A * G):
+            s = whisper_ref.process_logits(
+                lp[q], self._seqs[q], self._plen, suppress=o.suppress_tokens, begin_suppress=o.begin_suppress_tokens,
+                ts_rules=o.timestamp_rules, ts_begin=o.timestamp_begin, no_ts=o.no_timestamps_token, eos=o.eos_token,
+                max_initial_ts=o.max_initial_timestamp_index if o.max_initial_timestamp_index >= 0 else None)
+            order = np.argsort(-s, kind="stable")[:K]
+            cs[q] = s[order] + np.float32(run_scores[q])
+            ct[q] = np.where(np.isfinite(s[order]), order, -1)
+        return cs, ct
+
+    def decode_reorder(self, parent, next_token):
+        old = self._seqs
+        self._seqs = [list(old[int(p)]) + [int(t)] for p, t in zip(parent, next_token)]
 
     @torch.no_grad()
     def decode_run(self, n):
+        if getattr(self, "_G", 1) > 1:
+            return  # beam mode: decode_beam_step re-forwards the whole sequences
         ids = torch.from_numpy(self._prompts).long()
         out = self.model.model.decoder(input_ids=ids, encoder_hidden_states=self.enc[: self._A])
         self._logits = self.model.proj_out(out.last_hidden_state[:, -1]).float()

@@ -160,3 +160,16 @@ def test_window_schedule_matches_transformers():
         ref = [(it["stride"], it["is_last"]) for it in chunk_iter(x, fe, cl, sl, sr)]
         mine = [(stride, last) for _, _, stride, last in chunk_windows(n, cl, sl, sr)]
         assert mine == ref, (n, mine, ref)
+
+
+def test_beam_search_host_logic_matches_reference(monkeypatch):
+    """num_beams=5 through the product's beam bookkeeping (thewhisper_b200/beam.py) on the CPU stand-in engine
+    reproduces the real reference's beam-search transcription."""
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, "model_tiny10.json")))
+    pipe = _stub_pipeline(monkeypatch, meta["preset"], meta["layer_gain"], meta["chunk_s"], batch_size=4)
+    audio = S.synth_audio(meta["audio_s"], seed=2000)
+    gk = {"num_beams": 5, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": 32}
+    out = pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=4, generate_kwargs=dict(gk))
+    assert out["text"] == meta["pipeline"]["beam5"]["text"]

@@ -254,6 +254,7 @@ class WhisperEngine:
         o.record_alignment = int(opts.record_alignment)
         _lib.check(self.lib.bw_decode_begin(self.h, A, G, prompts.ctypes.data_as(C.c_void_p), plen, C.byref(o), self._stream()))
         self._Q = A * G
+        self._A = A
         self._plen = plen
 
     def decode_run(self, n_steps: int) -> None:
@@ -273,6 +274,16 @@ class WhisperEngine:
         next_token = np.ascontiguousarray(next_token, dtype=np.int32)
         _lib.check(self.lib.bw_decode_reorder(self.h, parent.ctypes.data_as(C.c_void_p), next_token.ctypes.data_as(C.c_void_p),
                                               self._stream()))
+
+    def decode_beam_step(self, run_scores: np.ndarray):
+        """One decoder step in beam mode: -> (cand_scores [Q, 2G] float32, cand_tokens [Q, 2G] int32)."""
+        Q, K = self._Q, 2 * (self._Q // max(1, self._A))
+        run = np.ascontiguousarray(run_scores, dtype=np.float32)
+        cs = np.empty((Q, K), dtype=np.float32)
+        ct = np.empty((Q, K), dtype=np.int32)
+        _lib.check(self.lib.bw_decode_beam_step(self.h, run.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p),
+                                                ct.ctypes.data_as(C.c_void_p), self._stream()))
+        return cs, ct
 
     def logits(self) -> torch.Tensor:
         return self.buffer("logits", torch.float32, (self.max_audios * self.max_beams, self.dims.vocab))[: self._Q]
