@@ -85,7 +85,9 @@ struct bw_engine {
   bool use_anc = false;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   cudaGraphExec_t cur_graph = nullptr;
-  bool no_graph = false, simt = false;
+  bool no_graph = false, simt = false, no_mega = false;
+  int num_sms = 148;
+  unsigned* mega_bar = nullptr;
   std::map<std::string, std::pair<void*, size_t>> buffers;
 };
 
@@ -203,6 +205,40 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
 // one decoder step for all Q sequences (enqueued on st; captured into a CUDA graph by the caller)
 int step_impl(bw_engine* e, cudaStream_t st) {
   const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, V = e->V, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
+  const long long self_layer0 = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
+  const long long cross_layer0 = (long long)e->cfg.max_audios * H * S * 64;
+  bool mega_done = false;
+  if (!e->no_mega && G == 1 && Q <= 8 && (int)e->dec.size() <= MEGA_MAXL) {
+    // persistent one-kernel step (decode_mega.cu); falls through to the per-op path when unsupported (-3)
+    MegaArgs m{};
+    for (size_t l = 0; l < e->dec.size(); ++l) {
+      const DecLayer& L = e->dec[l];
+      MegaLayer& o = m.layers[l];
+      o.ln1g = L.ln1g; o.ln1b = L.ln1b; o.bqkv = L.bqkv; o.bo = L.bo; o.ln2g = L.ln2g; o.ln2b = L.ln2b; o.xbq = L.xbq; o.xbo = L.xbo;
+      o.ln3g = L.ln3g; o.ln3b = L.ln3b; o.b1 = L.b1; o.b2 = L.b2;
+      o.wqkv = L.wqkv; o.wo = L.wo; o.xwq = L.xwq; o.xwo = L.xwo; o.w1 = L.w1; o.w2 = L.w2;
+      o.self_k = e->self_k + l * self_layer0; o.self_v = e->self_v + l * self_layer0;
+      o.cross_k = e->cross_k + l * cross_layer0; o.cross_v = e->cross_v + l * cross_layer0;
+      o.head_slots = (e->opts.record_alignment && e->cfg.n_align_heads > 0) ? e->head_slots + l * H : nullptr;
+    }
+    m.L = (int)e->dec.size(); m.D = D; m.H = H; m.ffn = ffn; m.V = V; m.S = S; m.Tmax = Tmax; m.Q = Q;
+    m.embed = e->embed; m.dec_pos = e->dec_pos; m.lnf_g = e->dec_lnf_g; m.lnf_b = e->dec_lnf_b;
+    m.tokens = e->tokens; m.pos = e->pos;
+    m.dx = e->dx; m.dqkv = e->dqkv; m.dattn = e->dattn; m.dq = e->dq; m.dh = e->dh; m.logits = e->logits;
+    m.part_o = e->part_o; m.part_ml = e->part_ml; m.xcounters = e->xcounters; m.bar = e->mega_bar;
+    int ns = e->num_sms / (Q * H);
+    const int ns_min = (S + 255) / 256;
+    if (ns < ns_min) ns = ns_min;
+    if (ns > XSPLIT) ns = XSPLIT;
+    m.nsplit = ns;
+    if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
+      m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
+    }
+    const int rc = launch_decode_mega(st, m, e->num_sms);
+    if (rc == 0) mega_done = true;
+    else if (rc != -3) return rc;
+  }
+  if (!mega_done) {
   if (int rc = launch_embed(st, e->embed, e->dec_pos, e->tokens, e->pos, e->dx, Q, D, Tmax)) return rc;
   const long long self_layer = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
   const long long cross_layer = (long long)e->cfg.max_audios * H * S * 64;
@@ -282,6 +318,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     g.out = e->logits + (long long)m0 * V; g.ldo = V;
     if (int rc = launch_gemv(st, g)) return rc;
   }
+  }  // !mega_done
   SelectArgs s;
   s.logits = e->logits; s.V = V; s.Q = Q; s.Tmax = Tmax; s.tokens = e->tokens; s.finished = e->finished; s.pos = e->pos;
   s.done_ctr = e->done_ctr; s.suppress_bits = e->sup_bits; s.begin_suppress_bits = e->bsup_bits;
@@ -358,6 +395,12 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
   e->Tmax = cfg->max_target_positions; e->Spad = (e->S + 7) / 8 * 8;
   const char* ng = getenv("BW_NO_GRAPH");
   e->no_graph = ng && ng[0] == '1';
+  const char* nm = getenv("BW_NO_MEGA");
+  e->no_mega = nm && nm[0] == '1';
+  {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) e->num_sms = sms;
+  }
   const char* impl = getenv("BW_GEMM_IMPL");
   e->simt = impl && strcmp(impl, "simt") == 0;
   *out = e;
@@ -447,6 +490,7 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
+  if (dalloc(e, "mega_bar", &e->mega_bar, 4)) return -1;
   if (dalloc(e, "xcounters", &e->xcounters, (size_t)A * H)) return -1;
   if (dalloc(e, "sup_bits", &e->sup_bits, (size_t)(V + 31) / 32)) return -1;
   if (dalloc(e, "bsup_bits", &e->bsup_bits, (size_t)(V + 31) / 32)) return -1;

@@ -76,6 +76,40 @@ struct SelectArgs {
   int* cand_tokens = nullptr;         // [Q, n_cand]
 };
 
+// ---- persistent one-kernel-per-step decoder (decode_mega.cu) ----
+struct MegaLayer {
+  const float *ln1g, *ln1b, *bqkv, *bo, *ln2g, *ln2b, *xbq, *xbo, *ln3g, *ln3b, *b1, *b2;
+  const bf16 *wqkv, *wo, *xwq, *xwo, *w1, *w2;
+  bf16 *self_k, *self_v;
+  const bf16 *cross_k, *cross_v;
+  const int* head_slots;  // [H] or null
+};
+
+constexpr int MEGA_MAXL = 32;
+
+struct MegaArgs {
+  // the per-layer pointer table travels in the kernel parameter block (constant bank, ~8 KB: CUDA >= 12.1 allows 32 KB),
+  // so no phase spends registers or a dependent global load on it
+  MegaLayer layers[MEGA_MAXL];
+  int L, D, H, ffn, V, S, Tmax, Q;
+  const bf16* embed;
+  const float* dec_pos;
+  const float *lnf_g, *lnf_b;
+  const int* tokens;
+  const int* pos;
+  float *dx, *dqkv, *dattn, *dq, *dh, *logits;
+  float *part_o, *part_ml;  // cross-attention partials [Q][H][nsplit][64], [..][2]
+  unsigned* xcounters;      // [Q*H]
+  unsigned* bar;
+  int nsplit;
+  // alignment (word timestamps)
+  float* align;
+  int Ha, Tcap, step_base;
+};
+
+// Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).
+int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
+
 int launch_gemv(cudaStream_t st, const GemvArgs& a);
 int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax);
 int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q);
