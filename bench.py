@@ -113,7 +113,7 @@ def run_reference(args, rank: int, world: int):
     torch.set_num_threads(cores)
     new_tokens = int(os.environ.get("BW_REF_TOKENS", "16"))
     model = S.make_hf_model(PRESET, seed=0)
-    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True)
+    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True, suppress_timestamps=True)
     fe, tok = S.make_feature_extractor(CHUNK_S), S.make_tokenizer()
     pipe = hf_ref.make_ref_pipeline(model, fe, tok, chunk_length_s=CHUNK_S, device="cpu")
     audio = S.synth_audio(CHUNK_S, seed=1000)
@@ -158,7 +158,7 @@ def main():
     import torch.distributed as dist
 
     from thewhisper_b200 import synthetic as S
-    from thewhisper_b200.engine import DecodeOptions, ModelDims, WhisperEngine, interpolate_positions, pack_weights
+    from thewhisper_b200.engine import DecodeOptions, ModelDims, pack_weights
 
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local)
@@ -167,38 +167,41 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- weights: rank 0 builds the random checkpoint, one NCCL broadcast at init, nothing per step
+    # ---- weights: rank 0 builds the random checkpoint, ONE NCCL broadcast at init, nothing per step
+    from thewhisper_b200.nvidia import ASRPipeline
+    from thewhisper_b200.parallel import broadcast_weights
+
     cfg = S.make_hf_config(PRESET)
     dims = ModelDims.from_hf_config(cfg)
+    gcfg = S.make_generation_config(PRESET, eos_suppressed=True, suppress_timestamps=True)
     t0 = time.time()
     if rank == 0:
         model = S.make_hf_model(PRESET, seed=0)
         sd = model.state_dict()
         weights = pack_weights(sd, dims, sd["model.encoder.embed_positions.weight"].float(), dev)
-        meta = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in weights.items()]
-        del model, sd
+        del sd
     else:
-        weights, meta = None, None
-    if world > 1:
-        box = [meta]
-        dist.broadcast_object_list(box, src=0)
-        meta = box[0]
-        if rank != 0:
-            weights = {k: torch.empty(shape, dtype=getattr(torch, dt), device=dev) for k, shape, dt in meta}
-        for k, _, _ in meta:
-            dist.broadcast(weights[k], src=0)
-        torch.cuda.synchronize()
+        from transformers import WhisperForConditionalGeneration
+
+        with torch.device("meta"):
+            model = WhisperForConditionalGeneration(cfg)  # shapes/config only; the weights arrive over NCCL
+        weights = None
+    model.generation_config = gcfg
+    weights = broadcast_weights(weights, dev)
+    torch.cuda.synchronize()
     t_weights = time.time() - t0
 
-    A = 1  # chunks per GPU per step (configs[1])
-    gcfg = S.make_generation_config(PRESET, eos_suppressed=True)
-    eng = WhisperEngine({}, dims, chunk_length_s=CHUNK_S, device=str(dev), max_audios=A, max_beams=1, weights=weights)
+    A = 1  # chunks per GPU per step (BASELINE.json configs[1])
+    pipe = ASRPipeline(model, feature_extractor=S.make_feature_extractor(CHUNK_S), tokenizer=S.make_tokenizer(),
+                       chunk_length_s=CHUNK_S, device=str(dev), batch_size=A, max_beams=1, weights=weights)
+    eng = pipe.engine
     opts = DecodeOptions(eos_token=S.EOS, pad_token=S.EOS, suppress_tokens=list(gcfg.suppress_tokens),
                          begin_suppress_tokens=list(gcfg.begin_suppress_tokens))
     prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]] * A, dtype=np.int32)
     pcm = np.stack([S.synth_audio(CHUNK_S, seed=1000 + rank * A + i) for i in range(A)])
     pcm_dev = torch.from_numpy(pcm).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": NEW_TOKENS}
 
     def step_resident():
         eng.logmel_device(pcm_dev, A)
@@ -207,12 +210,9 @@ def main():
         eng.decode_run(prompt.shape[1] - 1 + NEW_TOKENS)
 
     def step_e2e():
-        eng.logmel(pcm)  # pinned staging + H2D inside
-        eng.encode(A)
-        eng.decode_begin(prompt, A, 1, opts)
-        eng.decode_run(prompt.shape[1] - 1 + NEW_TOKENS)
-        toks, fin, pos = eng.decode_read()  # D2H of the ids
-        return toks
+        # the call a user of the reference makes: host PCM in, text out (pinned H2D, D2H of ids, detokenisation inside)
+        out = pipe([pcm[i] for i in range(A)], batch_size=A, generate_kwargs=dict(gk))
+        return out
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -258,8 +258,9 @@ def main():
 
     step_ms = float(np.median([decode_only() for _ in range(5)]))
     clocks = sampler.stop() if rank == 0 else None
-    toks = step_e2e()
-    assert toks.shape[0] == A and (toks[:, 4:4 + NEW_TOKENS] >= 0).all()
+    outs = step_e2e()
+    n_words = [len(o["text"].split()) for o in outs]
+    assert len(outs) == A and min(n_words) >= 1, n_words
 
     if rank != 0:
         if world > 1:
@@ -276,13 +277,14 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"whisper-{PRESET} dims (random weights), {A} x {CHUNK_S}s synthetic chunk per GPU, greedy, "
-                               f"{NEW_TOKENS} new tokens (EOS suppressed)", "chunks_per_gpu": A, "new_tokens": NEW_TOKENS,
+                               f"{NEW_TOKENS} new tokens (EOS and timestamp ids suppressed: fixed length)", "chunks_per_gpu": A, "new_tokens": NEW_TOKENS,
                    "parallelism": f"dp{world} (independent chunks, weights broadcast once in {t_weights:.1f}s)",
                    "l2": "256 MB flush write between timed iterations", "rtf": (ms_res / 1e3) / (CHUNK_S * A),
                    "rtfx": (CHUNK_S * A) / (ms_res / 1e3), "decode_only_tokens_per_sec": A * 1e3 / step_ms,
                    "published_reference_headline": "220 tok/s on L40s (README.md:19), other hardware"},
         "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": int(pcm.nbytes + prompt.nbytes),
-                "d2h_bytes_per_step": int(A * dims.max_target_positions * 4 + A * 4 + 4), "ms_per_step": ms_e2e,
+                "d2h_bytes_per_step": int((NEW_TOKENS // 32) * (A * dims.max_target_positions * 4 + A * 4 + 4)), "ms_per_step": ms_e2e,
+                "api": "thewhisper_b200.nvidia.ASRPipeline.__call__(list of host float32 arrays) -> text",
                 "rtf": (ms_e2e / 1e3) / (CHUNK_S * A)},
         "gpu_launches": args.steps * (n_enc_kernels + (3 + NEW_TOKENS) * n_dec_kernels + 3),
         "clocks": clocks,
@@ -312,7 +314,7 @@ def cpu_baseline():
     torch.set_num_threads(cores)
     nt = 8
     model = S.make_hf_model(PRESET, seed=0)
-    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True)
+    model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True, suppress_timestamps=True)
     pipe = hf_ref.make_ref_pipeline(model, S.make_feature_extractor(CHUNK_S), S.make_tokenizer(), chunk_length_s=CHUNK_S, device="cpu")
     audio = S.synth_audio(CHUNK_S, seed=1000)
     gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": nt}

@@ -540,16 +540,16 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   if (a.L > MEGA_MAXL || Q > 8 || a.D > 1280 || a.ffn > 5120 || a.D % 8 != 0 || a.Tmax > MAXKEYS) return -3;
   const int mb = Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8));
   const size_t smem = mega_smem_bytes(mb, a.ffn);
-  if (smem > 227 * 1024) return -3;
+  if (smem > 226 * 1024) return -3;  // 227 KB opt-in limit includes the few bytes of static smem
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
 #define BW_MEGA_CASE(MB)                                                                                              \
   case MB: {                                                                                                          \
-    static bool attr = false;                                                                                         \
-    if (!attr) {                                                                                                      \
-      BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                    \
+    static size_t attr = 0;                                                                                           \
+    if (smem > attr) {                                                                                                \
+      BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr = smem;                                                                                                    \
     }                                                                                                                 \
     decode_mega_kernel<MB><<<num_sms, MT, smem, st>>>(a);                                                             \
   } break;

@@ -291,8 +291,6 @@ constexpr int XK = 128;
 
 template <int GM>  // compile-time bound on the beams per audio (1 or MAXG)
 __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) {
-  __shared__ float sc[GM][XK];
-  __shared__ float redo[16][GM][64];
   __shared__ float red4[4];
   __shared__ float gm[GM], gl[GM];
   __shared__ unsigned is_last;
@@ -305,9 +303,11 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
   const bf16* kbase = a.kc + (((long long)au * a.H + h) * a.S + s0) * 64 + sub * 8;
   const bf16* vbase = a.vc + (((long long)au * a.H + h) * a.S + s0) * 64 + sub * 8;
 
-  extern __shared__ __align__(16) uint8_t dyn[];  // K slice [XK][128 B] | V slice [XK][128 B]
+  extern __shared__ __align__(16) uint8_t dyn[];  // K slice [XK][128 B] | V slice [XK][128 B] | sc [GM][XK] | redo [16][GM][64]
   uint8_t* sK = dyn;
   uint8_t* sV = dyn + XK * 128;
+  float (*sc)[XK] = reinterpret_cast<float (*)[XK]>(dyn + 2 * XK * 128);
+  float (*redo)[GM][64] = reinterpret_cast<float (*)[GM][64]>(dyn + 2 * XK * 128 + GM * XK * sizeof(float));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int kk = i * 16 + grp;
@@ -501,8 +501,15 @@ int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q) {
 int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A) {
   BW_CHECK(a.G >= 1 && a.G <= MAXG, "cross_attn: G=%d must be in 1..%d", a.G, MAXG);
   BW_CHECK(a.S <= XSPLIT * XK, "cross_attn: S=%d exceeds %d", a.S, XSPLIT * XK);
-  if (a.G == 1) cross_attn_kernel<1><<<dim3(XSPLIT, a.H, A), 128, 2 * XK * 128, st>>>(a);
-  else cross_attn_kernel<MAXG><<<dim3(XSPLIT, a.H, A), 128, 2 * XK * 128, st>>>(a);
+  constexpr size_t smem1 = 2 * XK * 128 + (size_t)(1 * XK + 16 * 1 * 64) * sizeof(float);
+  constexpr size_t smemG = 2 * XK * 128 + (size_t)(MAXG * XK + 16 * MAXG * 64) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemG));
+    attr = true;
+  }
+  if (a.G == 1) cross_attn_kernel<1><<<dim3(XSPLIT, a.H, A), 128, smem1, st>>>(a);
+  else cross_attn_kernel<MAXG><<<dim3(XSPLIT, a.H, A), 128, smemG, st>>>(a);
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }

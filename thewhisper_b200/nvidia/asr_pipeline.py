@@ -33,6 +33,7 @@ class ASRPipeline:
         revision = kwargs.pop("revision", "main")
         self.batch_size = int(kwargs.pop("batch_size", 1) or 1)
         self.max_beams = int(kwargs.pop("max_beams", 5))
+        preloaded = kwargs.pop("weights", None)  # packed device weights (e.g. received by NCCL broadcast from rank 0)
         if isinstance(model, str):
             # weights come from a HF checkpoint; `model_size` ("S"/"XL") selected a TensorRT engine flavour in the
             # reference (REF :47-56) -- here there is one engine, so it is accepted and ignored.
@@ -64,8 +65,8 @@ class ASRPipeline:
         if dev == "cuda":
             dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cuda:0"
         self.device = dev
-        self._state_dict = {k: v for k, v in model.state_dict().items()}
-        self._weights = None
+        self._state_dict = None if preloaded is not None else {k: v for k, v in model.state_dict().items()}
+        self._weights = preloaded
         self.engine: Optional[WhisperEngine] = None
         self._build_engine(self.batch_size)
         install_merge()

@@ -111,7 +111,7 @@ def make_hf_config(preset: str = "large-v3", max_source_positions: int = 1500):
     )
 
 
-def make_generation_config(preset: str = "large-v3", eos_suppressed: bool = False):
+def make_generation_config(preset: str = "large-v3", eos_suppressed: bool = False, suppress_timestamps: bool = False):
     from transformers import GenerationConfig
 
     p = PRESETS[preset]
@@ -119,6 +119,10 @@ def make_generation_config(preset: str = "large-v3", eos_suppressed: bool = Fals
     sup = default_suppress_tokens()
     if eos_suppressed:
         sup = sorted(set(sup + [EOS]))
+    if suppress_timestamps:
+        # throughput runs: a random checkpoint emits timestamp ids at random even without timestamps, which would send the
+        # (reference-faithful) seek loop into extra encode+decode passes; fixed-length runs mask them for every arm
+        sup = sorted(set(sup) | set(range(TIMESTAMP_BEGIN, VOCAB)))
     g = GenerationConfig(
         max_length=448,
         pad_token_id=EOS,
