@@ -246,9 +246,10 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     const DecLayer& L = e->dec[l];
     bf16* kc = e->self_k + l * self_layer;
     bf16* vc = e->self_v + l * self_layer;
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN1 + fused QKV projection (+ self-KV append)
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // LN1 + fused QKV projection (+ self-KV append)
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln1g; g.ln_b = L.ln1b;
       g.W = L.wqkv; g.N = 3 * D; g.K = D; g.bias = L.bqkv; g.alpha = 0.125f; g.alpha_cols = D;
       g.out = e->dqkv + (long long)m0 * 3 * D; g.ldo = 3 * D;
@@ -261,16 +262,18 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       s.H = H; s.D = D; s.Tmax = Tmax;
       if (int rc = launch_self_attn(st, s, Q)) return rc;
     }
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // out-proj + residual
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // out-proj + residual
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dattn + (long long)m0 * D; g.ldx = D; g.W = L.wo; g.N = D; g.K = D; g.bias = L.bo;
       g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
       if (int rc = launch_gemv(st, g)) return rc;
     }
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN2 + cross q projection
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // LN2 + cross q projection
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln2g; g.ln_b = L.ln2b;
       g.W = L.xwq; g.N = D; g.K = D; g.bias = L.xbq; g.alpha = 0.125f; g.alpha_cols = D;
       g.out = e->dq + (long long)m0 * D; g.ldo = D;
@@ -287,32 +290,36 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       }
       if (int rc = launch_cross_attn(st, c, A)) return rc;
     }
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // cross out-proj + residual
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // cross out-proj + residual
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dattn + (long long)m0 * D; g.ldx = D; g.W = L.xwo; g.N = D; g.K = D; g.bias = L.xbo;
       g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
       if (int rc = launch_gemv(st, g)) return rc;
     }
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // LN3 + fc1 + GELU
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // LN3 + fc1 + GELU
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = L.ln3g; g.ln_b = L.ln3b;
       g.W = L.w1; g.N = ffn; g.K = D; g.bias = L.b1; g.act = 1;
       g.out = e->dh + (long long)m0 * ffn; g.ldo = ffn;
       if (int rc = launch_gemv(st, g)) return rc;
     }
-    for (int m0 = 0; m0 < Q; m0 += 8) {  // fc2 + residual
+    for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // fc2 + residual
       GemvArgs g;
-      g.M = std::min(8, Q - m0);
+      g.M = Q - m0;
       g.x = e->dh + (long long)m0 * ffn; g.ldx = ffn; g.W = L.w2; g.N = D; g.K = ffn; g.bias = L.b2;
       g.residual = e->dx + (long long)m0 * D; g.out = e->dx + (long long)m0 * D; g.ldo = D;
       if (int rc = launch_gemv(st, g)) return rc;
     }
   }
-  for (int m0 = 0; m0 < Q; m0 += 8) {  // final LN + tied LM head
+  for (int m0 = 0; m0 < Q; m0 += Q) {  // (one launch: the kernel walks M in chunks of 8)
+       // final LN + tied LM head
     GemvArgs g;
-    g.M = std::min(8, Q - m0);
+    g.M = Q - m0;
     g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = e->dec_lnf_g; g.ln_b = e->dec_lnf_b;
     g.W = e->embed; g.N = V; g.K = D;
     g.out = e->logits + (long long)m0 * V; g.ldo = V;

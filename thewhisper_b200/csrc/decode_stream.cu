@@ -71,121 +71,130 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvArgs a, co
   WRegs<NC, R> cur;
   if (n_begin < n_end) load_rows<NC, R>(cur, a.W, K, n_begin, n_end, lane);
 
-  // 2) stage x (and LayerNorm it): two-pass, biased variance, eps 1e-5 like torch.nn.LayerNorm
-  for (int i = threadIdx.x; i < MB * K; i += GEMV_THREADS) {
-    const int m = i / K, k = i - m * K;
-    xs[i] = (m < a.M) ? a.x[(long long)m * a.ldx + k] : 0.f;
-  }
-  __syncthreads();
-  if (a.ln_g) {
-    float part[MB];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) part[m] = 0.f;
-    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
-#pragma unroll
-      for (int m = 0; m < MB; ++m) part[m] += xs[m * K + k];
-    }
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      const float s = warp_sum(part[m]);
-      if (lane == 0) red[warp][m] = s;
+  // 2) for every chunk of MB rows of x: stage (+ LayerNorm: two-pass, biased variance, eps 1e-5 like torch.nn.LayerNorm),
+  //    then all of this warp's weight rows against the chunk.  M > MB re-uses the weights already in registers, so a
+  //    batch streams each weight row from HBM once per launch instead of once per 8 sequences.
+  const int pos = a.pos ? *a.pos : 0;
+  const bool single_pass = (n_begin + R >= n_end);
+  for (int m0 = 0; m0 < a.M; m0 += MB) {
+    const int mrows = min(MB, a.M - m0);
+    __syncthreads();  // previous chunk's readers are done with xs
+    for (int i = threadIdx.x; i < MB * K; i += GEMV_THREADS) {
+      const int m = i / K, k = i - m * K;
+      xs[i] = (m < mrows) ? a.x[(long long)(m0 + m) * a.ldx + k] : 0.f;
     }
     __syncthreads();
-    if (threadIdx.x < MB) {
-      float s = 0.f;
-      for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
-      stat[0][threadIdx.x] = s / (float)K;
-    }
-    __syncthreads();
+    if (a.ln_g) {
+      float part[MB];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) part[m] = 0.f;
-    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+      for (int m = 0; m < MB; ++m) part[m] = 0.f;
+      for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m) part[m] += xs[m * K + k];
+      }
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
-        const float d = xs[m * K + k] - stat[0][m];
-        part[m] = fmaf(d, d, part[m]);
+        const float s = warp_sum(part[m]);
+        if (lane == 0) red[warp][m] = s;
       }
-    }
+      __syncthreads();
+      if (threadIdx.x < MB) {
+        float s = 0.f;
+        for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
+        stat[0][threadIdx.x] = s / (float)K;
+      }
+      __syncthreads();
 #pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      const float s = warp_sum(part[m]);
-      if (lane == 0) red[warp][m] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < MB) {
-      float s = 0.f;
-      for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
-      stat[1][threadIdx.x] = rsqrtf(s / (float)K + 1e-5f);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
-      const float g = a.ln_g[k], bb = a.ln_b[k];
-#pragma unroll
-      for (int m = 0; m < MB; ++m) xs[m * K + k] = (xs[m * K + k] - stat[0][m]) * stat[1][m] * g + bb;
-    }
-    __syncthreads();
-  }
-
-  const int pos = a.pos ? *a.pos : 0;
-  for (int n = n_begin; n < n_end; n += R) {
-    WRegs<NC, R> nxt;
-    const bool has_next = (n + R) < n_end;
-    if (PIPE && has_next) load_rows<NC, R>(nxt, a.W, K, n + R, n_end, lane);
-    float acc[R][MB];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const int k = lane * 8 + i * 256;
-      if (k < K) {
-        float wf[R][8];
-#pragma unroll
-        for (int r = 0; r < R; ++r) unpack8(cur.w[r][i], wf[r]);
+      for (int m = 0; m < MB; ++m) part[m] = 0.f;
+      for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
-          const float4 xa = *reinterpret_cast<const float4*>(&xs[m * K + k]);
-          const float4 xb = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            float s = acc[r][m];
-            s = fmaf(wf[r][0], xa.x, s); s = fmaf(wf[r][1], xa.y, s); s = fmaf(wf[r][2], xa.z, s); s = fmaf(wf[r][3], xa.w, s);
-            s = fmaf(wf[r][4], xb.x, s); s = fmaf(wf[r][5], xb.y, s); s = fmaf(wf[r][6], xb.z, s); s = fmaf(wf[r][7], xb.w, s);
-            acc[r][m] = s;
-          }
+          const float d = xs[m * K + k] - stat[0][m];
+          part[m] = fmaf(d, d, part[m]);
         }
       }
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const float s = warp_sum(part[m]);
+        if (lane == 0) red[warp][m] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x < MB) {
+        float s = 0.f;
+        for (int w = 0; w < GEMV_WARPS; ++w) s += red[w][threadIdx.x];
+        stat[1][threadIdx.x] = rsqrtf(s / (float)K + 1e-5f);
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+        const float g = a.ln_g[k], bb = a.ln_b[k];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) xs[m * K + k] = (xs[m * K + k] - stat[0][m]) * stat[1][m] * g + bb;
+      }
+      __syncthreads();
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int m = 0; m < MB; ++m) acc[r][m] = warp_sum(acc[r][m]);
-    // lanes [16r, 16r + MB) finish row n + r
-    const int m = lane & 15, r_sel = lane >> 4;
-    const int nn = n + r_sel;
-    if (r_sel < R && m < MB && m < a.M && nn < n_end) {
-      float v = 0.f;
+    // (multi-pass launches -- the LM head -- are only issued with M <= MB, so `cur` is reloaded per chunk only then)
+    if (m0 > 0 && !single_pass && n_begin < n_end) load_rows<NC, R>(cur, a.W, K, n_begin, n_end, lane);
+    for (int n = n_begin; n < n_end; n += R) {
+      WRegs<NC, R> nxt;
+      const bool has_next = (n + R) < n_end;
+      if (PIPE && has_next) load_rows<NC, R>(nxt, a.W, K, n + R, n_end, lane);
+      float acc[R][MB];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int mm = 0; mm < MB; ++mm)
-          if (r == r_sel && mm == m) v = acc[r][mm];
-      if (a.bias) v += a.bias[nn];
-      if (nn < a.alpha_cols) v *= a.alpha;
-      if (a.act == 1) v = gelu_erf(v);
-      if (a.residual) v += a.residual[(long long)m * a.ldo + nn];
-      a.out[(long long)m * a.ldo + nn] = v;
-      if (a.kc && nn >= a.D) {
-        const long long row = ((long long)(a.seq0 + m) * a.Tmax + pos) * a.D;
-        if (nn < 2 * a.D) a.kc[row + nn - a.D] = __float2bfloat16(v);
-        else a.vc[row + nn - 2 * a.D] = __float2bfloat16(v);
+        for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int k = lane * 8 + i * 256;
+        if (k < K) {
+          float wf[R][8];
+#pragma unroll
+          for (int r = 0; r < R; ++r) unpack8(cur.w[r][i], wf[r]);
+#pragma unroll
+          for (int m = 0; m < MB; ++m) {
+            const float4 xa = *reinterpret_cast<const float4*>(&xs[m * K + k]);
+            const float4 xb = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              float s = acc[r][m];
+              s = fmaf(wf[r][0], xa.x, s); s = fmaf(wf[r][1], xa.y, s); s = fmaf(wf[r][2], xa.z, s); s = fmaf(wf[r][3], xa.w, s);
+              s = fmaf(wf[r][4], xb.x, s); s = fmaf(wf[r][5], xb.y, s); s = fmaf(wf[r][6], xb.z, s); s = fmaf(wf[r][7], xb.w, s);
+              acc[r][m] = s;
+            }
+          }
+        }
       }
-    }
-    if (PIPE) {
-      if (has_next) cur = nxt;
-    } else if (has_next) {
-      load_rows<NC, R>(cur, a.W, K, n + R, n_end, lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) acc[r][m] = warp_sum(acc[r][m]);
+      // lanes [16r, 16r + MB) finish row n + r
+      const int m = lane & 15, r_sel = lane >> 4;
+      const int nn = n + r_sel;
+      if (r_sel < R && m < mrows && nn < n_end) {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int mm = 0; mm < MB; ++mm)
+            if (r == r_sel && mm == m) v = acc[r][mm];
+        const int mg = m0 + m;
+        if (a.bias) v += a.bias[nn];
+        if (nn < a.alpha_cols) v *= a.alpha;
+        if (a.act == 1) v = gelu_erf(v);
+        if (a.residual) v += a.residual[(long long)mg * a.ldo + nn];
+        a.out[(long long)mg * a.ldo + nn] = v;
+        if (a.kc && nn >= a.D) {
+          const long long row = ((long long)(a.seq0 + mg) * a.Tmax + pos) * a.D;
+          if (nn < 2 * a.D) a.kc[row + nn - a.D] = __float2bfloat16(v);
+          else a.vc[row + nn - 2 * a.D] = __float2bfloat16(v);
+        }
+      }
+      if (PIPE) {
+        if (has_next) cur = nxt;
+      } else if (has_next) {
+        load_rows<NC, R>(cur, a.W, K, n + R, n_end, lane);
+      }
     }
   }
 }
@@ -477,12 +486,12 @@ int launch_gemv_mb(cudaStream_t st, const GemvArgs& a) {
 }  // namespace
 
 int launch_gemv(cudaStream_t st, const GemvArgs& a) {
-  BW_CHECK(a.M >= 1 && a.M <= 8, "gemv: M=%d must be in 1..8", a.M);
+  BW_CHECK(a.M >= 1, "gemv: M=%d must be >= 1", a.M);
   BW_CHECK(a.K % 8 == 0 && a.K <= 5120, "gemv: K=%d must be a multiple of 8 and <= 5120", a.K);
   if (a.M <= 1) return launch_gemv_mb<1>(st, a);
   if (a.M <= 2) return launch_gemv_mb<2>(st, a);
   if (a.M <= 4) return launch_gemv_mb<4>(st, a);
-  return launch_gemv_mb<8>(st, a);
+  return launch_gemv_mb<8>(st, a);  // M > 8: the kernel walks the rows in chunks of 8 with the weights held in registers
 }
 
 int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q) {
