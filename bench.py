@@ -109,7 +109,7 @@ def run_reference(args, rank: int, world: int):
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
 
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)  # more threads than this make the HF CPU path slower, not faster
     torch.set_num_threads(cores)
     new_tokens = int(os.environ.get("BW_REF_TOKENS", "16"))
     model = S.make_hf_model(PRESET, seed=0)
@@ -310,7 +310,7 @@ def cpu_baseline():
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
 
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)  # HF/oneDNN on 128 threads is several times slower than on 32 (oversubscription)
     torch.set_num_threads(cores)
     nt = 8
     model = S.make_hf_model(PRESET, seed=0)
