@@ -1,16 +1,24 @@
-// One persistent kernel per decoder step (q_len = 1, up to 8 sequences, one beam per audio).
+// One persistent kernel per decoder step (q_len = 1, one beam per audio, up to 2 sequences).
 //
-// Why: with one kernel per op the step is 259 launches; on B200 each kernel boundary costs ~4 us of drain + launch and
-// exposes one DRAM round trip, so a step that should take 0.32 ms (2.07 GB at the measured 6.5 TB/s) took 1.7 ms
+// Why: with one kernel per op the step is 259 launches and every op pays its own chain of dependent global round
+// trips; a step that should take 0.32 ms (2.07 GB at the measured 6.5 TB/s) took 1.7 ms
 // (profiles/r1_v1_launches_summary.md).  Here the whole step -- embedding, 32 x (LN1+QKV, self-attention, out-proj,
 // LN2+cross-q, cross-attention, out-proj, LN3+fc1+GELU, fc2), final LN + tied LM head -- runs in ONE kernel of one CTA
-// per SM.  Phases are separated by a grid barrier (~1 us, a global atomic counter), and every phase requests its first
-// weight rows BEFORE waiting at the barrier that precedes it, so the DRAM latency of phase p+1 hides behind the tail of
-// phase p and the barrier itself.  Token selection stays a separate small kernel (select_kernel).
+// per SM, phases separated by a grid barrier.
 //
-// Work split: 16 warps per CTA, global warp id gw; a GEMV phase gives warp gw the rows {gw*R + i*GW*R + r}; attention
-// phases hand (sequence, head[, key split]) items to CTAs round-robin.  Activations that cross CTAs (dx, dqkv, dattn, dq, dh,
-// partials) are read with ld.global.cg (L2) because L1 is not coherent across SMs; weights use ld.global.nc.
+// The cost model that shaped it (ncu of the first version, profiles/r1_v2_*): 60% of all stall samples were warps parked
+// at the barrier -- a phase is only as fast as its chain of *dependent* L2/DRAM round trips (~0.6-1 us each), not its
+// bytes.  So everything that does not depend on the previous phase is requested BEFORE the barrier that precedes a phase:
+//   * the phase's weight rows (ld.global.nc into registers: all rows of the phase are in flight at once) and bias values,
+//   * its LayerNorm gamma/beta and the attention K/V rows that are already final (cp.async into smem),
+//   * the barrier itself is one red.release + ld.acquire polling loop (no membar.sc / L1 invalidation; activations that
+//     cross CTAs are read with ld.global.cg),
+//   * LayerNorm statistics are computed redundantly by every warp from the staged row (no block reductions), and the
+//     normalisation is applied on the fly inside the dot product.
+// After a barrier only the x row (and the residual values of the rows a warp owns) have to be fetched.
+//
+// Work split: 12 warps per CTA, global warp id gw; a GEMV phase gives warp gw the rows {gw*R + i*GW*R + r}; attention
+// phases hand (sequence, head[, key split]) items to CTAs round-robin.  Token selection stays a separate small kernel.
 #include <math.h>
 
 #include "decode.cuh"
@@ -20,11 +28,12 @@ namespace bw {
 
 namespace {
 
-constexpr int MT = 384;        // threads per CTA (12 warps: <= 170 registers per thread, no spills)
+constexpr int MT = 384;        // threads per CTA (12 warps: <= 170 registers per thread)
 constexpr int MW = MT / 32;    // warps per CTA
 constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
 constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
 constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
+constexpr int MAXD = 1280;
 
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
   float2 t;
@@ -42,8 +51,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-// grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel)
+// grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel).  bar.sync orders
+// the CTA's writes before thread 0's release; the acquire poll + bar.sync orders the other CTAs' writes before our reads.
 struct GridBar {
   unsigned* ctr;
   unsigned nblocks;
@@ -52,17 +65,17 @@ struct GridBar {
     __syncthreads();
     if (threadIdx.x == 0) {
       ++epoch;
-      __threadfence();
-      atomicAdd(ctr, 1u);
+      red_release_add(ctr, 1u);
       const unsigned target = epoch * nblocks;
-      const long long t0 = clock64();
-      while (ld_acquire_u32(ctr) < target) {
-        if (clock64() - t0 > (1ll << 32)) {
-          printf("[bw] decode_mega: grid barrier %u timed out (block %d)\n", epoch, blockIdx.x);
-          __trap();
+      if (ld_acquire_u32(ctr) < target) {
+        const long long t0 = clock64();
+        while (ld_acquire_u32(ctr) < target) {
+          if (clock64() - t0 > (1ll << 32)) {
+            printf("[bw] decode_mega: grid barrier %u timed out (block %d)\n", epoch, blockIdx.x);
+            __trap();
+          }
         }
       }
-      __threadfence();
     }
     __syncthreads();
   }
@@ -71,10 +84,12 @@ struct GridBar {
 template <int NC, int R>
 struct WR {
   uint4 w[R][NC];
+  float bias[R];
 };
 
 template <int NC, int R>
-__device__ __forceinline__ void load_rows_m(WR<NC, R>& wr, const bf16* __restrict__ W, int K, int n, int N, int lane) {
+__device__ __forceinline__ void load_rows_m(WR<NC, R>& wr, const bf16* __restrict__ W, const float* __restrict__ bias, int K, int n,
+                                            int N, int lane) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int row = min(n + r, N - 1);
@@ -84,15 +99,28 @@ __device__ __forceinline__ void load_rows_m(WR<NC, R>& wr, const bf16* __restric
       const int k = lane * 8 + i * 256;
       wr.w[r][i] = (k < K) ? ld_nc_u4(wp + k) : make_uint4(0u, 0u, 0u, 0u);
     }
+    wr.bias[r] = bias ? bias[row] : 0.f;
+  }
+}
+
+template <int NC, int R>
+__device__ __forceinline__ void prefetch_rows(WR<NC, R>& w, const bf16* W, const float* bias, int N, int K, int gw, int lane) {
+  if (gw * R < N) load_rows_m<NC, R>(w, W, bias, K, gw * R, N, lane);
+}
+
+// LayerNorm gamma/beta of the NEXT LN phase -> smem (double buffered), requested before the barrier
+__device__ __forceinline__ void prefetch_gb(float* gb, const float* __restrict__ g, const float* __restrict__ b, int D) {
+  for (int i = threadIdx.x * 4; i < D; i += MT * 4) {
+    cp_async16m(gb + i, g + i);
+    cp_async16m(gb + MAXD + i, b + i);
   }
 }
 
 struct PhaseOut {
-  const float* bias;
   float alpha;
   int alpha_cols;
   int act;
-  float* residual;  // may alias out
+  const float* residual;  // may alias out
   float* out;
   int ldo;
   bf16* kc;  // optional KV scatter (fused QKV)
@@ -100,77 +128,56 @@ struct PhaseOut {
   int D, Tmax, pos;
 };
 
-// stage M rows of K floats into smem (ld.global.cg), optionally LayerNorm them.  All MT threads.
+// stage M rows of K floats into smem (ld.global.cg).  With `ln`, every warp then derives mean / rstd of each row on its own
+// (two passes over smem, no block reduction); the normalisation itself happens inside the dot product.
 template <int MB>
-__device__ void stage_x(float* xs, float* red, const float* __restrict__ src, int ld, int K, int M, const float* __restrict__ g,
-                        const float* __restrict__ b) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < MB * K; i += MT) {
+__device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src, int ld, int K, int M, bool ln, float (&mean)[MB],
+                                        float (&rstd)[MB]) {
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x * 4; i < MB * K; i += MT * 4) {
     const int m = i / K, k = i - m * K;
-    xs[i] = (m < M) ? __ldcg(src + (long long)m * ld + k) : 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) v = __ldcg(reinterpret_cast<const float4*>(src + (long long)m * ld + k));
+    *reinterpret_cast<float4*>(xs + i) = v;
   }
+  cp_async_wait_allm();  // gamma/beta (and anything else this thread prefetched) have landed
   __syncthreads();
-  if (!g) return;
-  float part[MB];
-#pragma unroll
-  for (int m = 0; m < MB; ++m) part[m] = 0.f;
-  for (int k = threadIdx.x; k < K; k += MT) {
-#pragma unroll
-    for (int m = 0; m < MB; ++m) part[m] += xs[m * K + k];
-  }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
-    const float s = warp_sum(part[m]);
-    if (lane == 0) red[warp * MB + m] = s;
+    mean[m] = 0.f;
+    rstd[m] = 1.f;
   }
-  __syncthreads();
-  float mean[MB];
+  if (!ln) return;
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     float s = 0.f;
-    for (int w = 0; w < MW; ++w) s += red[w * MB + m];
-    mean[m] = s / (float)K;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int m = 0; m < MB; ++m) part[m] = 0.f;
-  for (int k = threadIdx.x; k < K; k += MT) {
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      const float d = xs[m * K + k] - mean[m];
-      part[m] = fmaf(d, d, part[m]);
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + m * K + k);
+      s += (v.x + v.y) + (v.z + v.w);
     }
+    const float mu = warp_sum(s) / (float)K;
+    float ss = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + m * K + k);
+      const float a0 = v.x - mu, a1 = v.y - mu, a2 = v.z - mu, a3 = v.w - mu;
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    mean[m] = mu;
+    rstd[m] = rsqrtf(warp_sum(ss) / (float)K + 1e-5f);
   }
-#pragma unroll
-  for (int m = 0; m < MB; ++m) {
-    const float s = warp_sum(part[m]);
-    if (lane == 0) red[warp * MB + m] = s;
-  }
-  __syncthreads();
-  float rstd[MB];
-#pragma unroll
-  for (int m = 0; m < MB; ++m) {
-    float s = 0.f;
-    for (int w = 0; w < MW; ++w) s += red[w * MB + m];
-    rstd[m] = rsqrtf(s / (float)K + 1e-5f);
-  }
-  for (int k = threadIdx.x; k < K; k += MT) {
-    const float gg = g[k], bb = b[k];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) xs[m * K + k] = (xs[m * K + k] - mean[m]) * rstd[m] * gg + bb;
-  }
-  __syncthreads();
 }
 
 // rows {gw*R + i*GW*R + r}; `cur` already holds the first pass (prefetched before the preceding barrier)
 template <int MB, int NC, int R, bool PIPE>
-__device__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, int N, int K, const float* xs, int M, const PhaseOut& o, int gw,
-                           int GW, int lane) {
+__device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K,
+                                           const float* xs, const float* gb, const float (&mean)[MB], const float (&rstd)[MB], int M,
+                                           const PhaseOut& o, float res0, int gw, int GW, int lane) {
+  bool first = true;
   for (int n = gw * R; n < N; n += GW * R) {
     WR<NC, R> nxt;  // (dead when !PIPE)
     const int n2 = n + GW * R;
     const bool has_next = n2 < N;
-    if (PIPE && has_next) load_rows_m<NC, R>(nxt, W, K, n2, N, lane);
+    if (PIPE && has_next) load_rows_m<NC, R>(nxt, W, bias, K, n2, N, lane);
     float acc[R][MB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -183,15 +190,27 @@ __device__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, int N, in
         float wf[R][8];
 #pragma unroll
         for (int r = 0; r < R; ++r) unpack8m(cur.w[r][i], wf[r]);
+        float g[8], b[8];
+        if (gb) {
+          *reinterpret_cast<float4*>(&g[0]) = *reinterpret_cast<const float4*>(gb + k);
+          *reinterpret_cast<float4*>(&g[4]) = *reinterpret_cast<const float4*>(gb + k + 4);
+          *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(gb + MAXD + k);
+          *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(gb + MAXD + k + 4);
+        }
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
-          const float4 xa = *reinterpret_cast<const float4*>(&xs[m * K + k]);
-          const float4 xb = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
+          float x[8];
+          *reinterpret_cast<float4*>(&x[0]) = *reinterpret_cast<const float4*>(&xs[m * K + k]);
+          *reinterpret_cast<float4*>(&x[4]) = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
+          if (gb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (x[j] - mean[m]) * rstd[m] * g[j] + b[j];
+          }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             float s = acc[r][m];
-            s = fmaf(wf[r][0], xa.x, s); s = fmaf(wf[r][1], xa.y, s); s = fmaf(wf[r][2], xa.z, s); s = fmaf(wf[r][3], xa.w, s);
-            s = fmaf(wf[r][4], xb.x, s); s = fmaf(wf[r][5], xb.y, s); s = fmaf(wf[r][6], xb.z, s); s = fmaf(wf[r][7], xb.w, s);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(wf[r][j], x[j], s);
             acc[r][m] = s;
           }
         }
@@ -204,16 +223,18 @@ __device__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, int N, in
     const int m = lane & 7, r_sel = lane >> 3;  // lanes [8r, 8r + MB) finish row n + r  (R <= 4, MB <= 8)
     const int nn = n + r_sel;
     if (r_sel < R && m < MB && m < M && nn < N) {
-      float v = 0.f;
+      float v = 0.f, bv = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r) {
+        if (r == r_sel) bv = cur.bias[r];
 #pragma unroll
         for (int mm = 0; mm < MB; ++mm)
           if (r == r_sel && mm == m) v = acc[r][mm];
-      if (o.bias) v += o.bias[nn];
+      }
+      v += bv;
       if (nn < o.alpha_cols) v *= o.alpha;
       if (o.act == 1) v = gelu_erf(v);
-      if (o.residual) v += __ldcg(o.residual + (long long)m * o.ldo + nn);
+      if (o.residual) v += first ? res0 : __ldcg(o.residual + (long long)m * o.ldo + nn);
       o.out[(long long)m * o.ldo + nn] = v;
       if (o.kc && nn >= o.D) {
         const long long row = ((long long)m * o.Tmax + o.pos) * o.D;
@@ -221,17 +242,23 @@ __device__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, int N, in
         else o.vc[row + nn - 2 * o.D] = __float2bfloat16(v);
       }
     }
+    first = false;
     if (PIPE) {
       if (has_next) cur = nxt;
     } else if (has_next) {
-      load_rows_m<NC, R>(cur, W, K, n2, N, lane);
+      load_rows_m<NC, R>(cur, W, bias, K, n2, N, lane);
     }
   }
 }
 
-template <int NC, int R>
-__device__ __forceinline__ void prefetch_rows(WR<NC, R>& w, const bf16* W, int N, int K, int gw, int lane) {
-  if (gw * R < N) load_rows_m<NC, R>(w, W, K, gw * R, N, lane);
+// the residual value of the output element this lane will finish in the first pass (fetched right after the barrier so
+// its L2 round trip overlaps the x staging)
+template <int MB, int R>
+__device__ __forceinline__ float fetch_residual(const float* residual, int ldo, int N, int M, int gw, int lane) {
+  const int m = lane & 7, r_sel = lane >> 3;
+  const int nn = gw * R + r_sel;
+  if (residual && r_sel < R && m < MB && m < M && nn < N) return __ldcg(residual + (long long)m * ldo + nn);
+  return 0.f;
 }
 
 __device__ __forceinline__ float block_max_m(float v, float* red) {
@@ -255,13 +282,14 @@ __device__ __forceinline__ float block_sum_m(float v, float* red) {
   return r;
 }
 
-// smem carve-up (dynamic): red [MW*8 + 64] floats | union { xs [MB*ffn] floats (GEMV phases), attention scratch }
+// smem carve-up (dynamic): red [32] | xs [MB*ffn] | gb [2][2*MAXD] | attention scratch (K rows, V rows, scores, partial out)
 template <int MB>
 __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
   extern __shared__ __align__(16) uint8_t dyn[];
   float* red = reinterpret_cast<float*>(dyn);
-  float* xs = red + MW * 8 + 64;
-  uint8_t* att = reinterpret_cast<uint8_t*>(xs);  // attention phases never overlap a GEMV phase
+  float* xs = red + 32;
+  float* gbuf = xs + (size_t)MB * a.ffn;
+  uint8_t* att = reinterpret_cast<uint8_t*>(gbuf + 4 * MAXD);
   __shared__ unsigned s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,11 +297,18 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int D = a.D, H = a.H, Q = a.Q, ffn = a.ffn;
   const int pos = *a.pos;
   GridBar bar{a.bar, gridDim.x, 0u};
+  float mean[MB], rstd[MB];
+  int gsel = 0;  // which gamma/beta buffer the next LN phase uses
 
-  // ---- phase 0: embedding (CTA 0 writes the residual stream), first QKV rows requested meanwhile
+  const int nsplit = a.nsplit;
+  const int ks = (a.S + nsplit - 1) / nsplit;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // KG key groups x 8 lanes
+
+  // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   WR<5, 3> w53;  // QKV and fc1: 3 rows per warp (1776 warps x 3 >= 5120 rows: one pass)
   WR<5, 2> w52;  // out-proj / cross-q / LM head
-  prefetch_rows<5, 3>(w53, a.layers[0].wqkv, 3 * D, D, gw, lane);
+  prefetch_rows<5, 3>(w53, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, lane);
+  prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[0].ln1g, a.layers[0].ln1b, D);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
@@ -286,31 +321,47 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   for (int l = 0; l < a.L; ++l) {
     const MegaLayer& L = a.layers[l];
     // ---------------- A: LN1 + fused QKV (+ self-KV append) ----------------
-    stage_x<MB>(xs, red, a.dx, D, D, Q, L.ln1g, L.ln1b);
+    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
-      PhaseOut o{L.bqkv, 0.125f, D, 0, nullptr, a.dqkv, 3 * D, L.self_k, L.self_v, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(w53, L.wqkv, 3 * D, D, xs, Q, o, gw, GW, lane);
+      PhaseOut o{0.125f, D, 0, nullptr, a.dqkv, 3 * D, L.self_k, L.self_v, D, a.Tmax, pos};
+      gemv_phase<MB, 5, 3, false>(w53, L.wqkv, L.bqkv, 3 * D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
     }
-    prefetch_rows<5, 2>(w52, L.wo, D, D, gw, lane);
+    gsel ^= 1;
+    prefetch_rows<5, 2>(w52, L.wo, L.bo, D, D, gw, lane);
+    // past K/V rows of this CTA's self-attention item do not depend on this step: request them now
+    if (blockIdx.x < Q * H) {
+      const int q = blockIdx.x / H, h = blockIdx.x - q * H;
+      uint8_t* sK = att;
+      uint8_t* sV = att + (size_t)MAXKEYS * 128;
+      for (int s = grp; s < pos; s += KG) {
+        const long long off = ((long long)q * a.Tmax + s) * D + h * 64 + sub * 8;
+        cp_async16m(sK + s * 128 + sub * 16, L.self_k + off);
+        cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
+      }
+    }
     bar.sync();
     // ---------------- B: causal self-attention, one (sequence, head) per CTA ----------------
     for (int item = blockIdx.x; item < Q * H; item += gridDim.x) {
       const int q = item / H, h = item - q * H;
       const int n = pos + 1;
-      const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // KG key groups x 8 lanes
       uint8_t* sK = att;
       uint8_t* sV = att + (size_t)MAXKEYS * 128;
       float* sc = reinterpret_cast<float*>(att + (size_t)MAXKEYS * 256);
       float* redo = sc + MAXKEYS;  // [KG][64]
-      for (int s = grp; s < n; s += KG) {
+      const int s_first = (item == blockIdx.x) ? pos : 0;  // rows < pos of the first item were prefetched
+      for (int s = s_first + grp; s < n; s += KG) {
         const long long off = ((long long)q * a.Tmax + s) * D + h * 64 + sub * 8;
         cp_async16m(sK + s * 128 + sub * 16, L.self_k + off);
         cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
       }
       float qv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qv[j] = __ldcg(a.dqkv + (long long)q * 3 * D + h * 64 + sub * 8 + j);
+      {
+        const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dqkv + (long long)q * 3 * D + h * 64 + sub * 8));
+        const float4 q1 = __ldcg(reinterpret_cast<const float4*>(a.dqkv + (long long)q * 3 * D + h * 64 + sub * 8 + 4));
+        qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+      }
       cp_async_wait_allm();
+      __syncthreads();  // the row of position `pos` was copied by group 0, whatever group reads it below
       float lmax = -INFINITY;
       for (int sb = 0; sb < n; sb += KG) {
         const int s = sb + grp;
@@ -359,26 +410,41 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     }
     bar.sync();
     // ---------------- C: self out-proj + residual ----------------
-    stage_x<MB>(xs, red, a.dattn, D, D, Q, nullptr, nullptr);
     {
-      PhaseOut o{L.bo, 1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.wo, D, D, xs, Q, o, gw, GW, lane);
+      const float res0 = fetch_residual<MB, 2>(a.dx, D, D, Q, gw, lane);
+      stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
+      gemv_phase<MB, 5, 2, false>(w52, L.wo, L.bo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
     }
-    prefetch_rows<5, 2>(w52, L.xwq, D, D, gw, lane);
+    prefetch_rows<5, 2>(w52, L.xwq, L.xbq, D, D, gw, lane);
+    prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln2g, L.ln2b, D);
     bar.sync();
     // ---------------- D: LN2 + cross q projection ----------------
-    stage_x<MB>(xs, red, a.dx, D, D, Q, L.ln2g, L.ln2b);
+    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
-      PhaseOut o{L.xbq, 0.125f, D, 0, nullptr, a.dq, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.xwq, D, D, xs, Q, o, gw, GW, lane);
+      PhaseOut o{0.125f, D, 0, nullptr, a.dq, D, nullptr, nullptr, D, a.Tmax, pos};
+      gemv_phase<MB, 5, 2, false>(w52, L.xwq, L.xbq, D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
     }
-    prefetch_rows<5, 2>(w52, L.xwo, D, D, gw, lane);
+    gsel ^= 1;
+    prefetch_rows<5, 2>(w52, L.xwo, L.xbo, D, D, gw, lane);
+    // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
+    if (blockIdx.x < Q * H * nsplit) {
+      const int item = blockIdx.x;
+      const int split = item % nsplit, h = (item / nsplit) % H, q = item / (nsplit * H);
+      const int s0 = split * ks;
+      const int n = max(0, min(a.S, s0 + ks) - s0);
+      const bf16* kbase = L.cross_k + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
+      const bf16* vbase = L.cross_v + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
+      uint8_t* sK = att;
+      uint8_t* sV = att + XKMAX * 128;
+      for (int kk = grp; kk < n; kk += KG) {
+        cp_async16m(sK + kk * 128 + sub * 16, kbase + (long long)kk * 64);
+        cp_async16m(sV + kk * 128 + sub * 16, vbase + (long long)kk * 64);
+      }
+    }
     bar.sync();
     // ---------------- E: cross-attention, (audio, head, key split) items; last split of a head merges ----------------
     {
-      const int nsplit = a.nsplit;
-      const int ks = (a.S + nsplit - 1) / nsplit;
-      const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
       uint8_t* sK = att;
       uint8_t* sV = att + XKMAX * 128;
       float* sc = reinterpret_cast<float*>(att + 2 * XKMAX * 128);
@@ -389,22 +455,27 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         const int q = item / (nsplit * H);
         const int s0 = split * ks;
         const int n = max(0, min(a.S, s0 + ks) - s0);
-        const bf16* kbase = L.cross_k + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
-        const bf16* vbase = L.cross_v + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
-        for (int kk = grp; kk < n; kk += KG) {
-          cp_async16m(sK + kk * 128 + sub * 16, kbase + (long long)kk * 64);
-          cp_async16m(sV + kk * 128 + sub * 16, vbase + (long long)kk * 64);
+        if (item != blockIdx.x) {  // later items of this CTA were not prefetched
+          const bf16* kbase = L.cross_k + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
+          const bf16* vbase = L.cross_v + (((long long)q * H + h) * a.S + s0) * 64 + sub * 8;
+          for (int kk = grp; kk < n; kk += KG) {
+            cp_async16m(sK + kk * 128 + sub * 16, kbase + (long long)kk * 64);
+            cp_async16m(sV + kk * 128 + sub * 16, vbase + (long long)kk * 64);
+          }
         }
         float qv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) qv[j] = __ldcg(a.dq + (long long)q * D + h * 64 + sub * 8 + j);
+        {
+          const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dq + (long long)q * D + h * 64 + sub * 8));
+          const float4 q1 = __ldcg(reinterpret_cast<const float4*>(a.dq + (long long)q * D + h * 64 + sub * 8 + 4));
+          qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+        }
         float* align_row = nullptr;
         if (a.align && L.head_slots) {
           const int slot = L.head_slots[h];
           const int step = pos - a.step_base;
           if (slot >= 0 && step >= 0 && step < a.Tcap) align_row = a.align + (((long long)q * a.Ha + slot) * a.Tcap + step) * a.S + s0;
         }
-        cp_async_wait_allm();
+        cp_async_wait_allm();  // (same thread -> piece map as the prefetch: each thread reads back its own copies)
         float lmax = -INFINITY;
         for (int kb = 0; kb < n; kb += KG) {
           const int kk = kb + grp;
@@ -489,56 +560,63 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     }
     bar.sync();
     // ---------------- F: cross out-proj + residual ----------------
-    stage_x<MB>(xs, red, a.dattn, D, D, Q, nullptr, nullptr);
     {
-      PhaseOut o{L.xbo, 1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.xwo, D, D, xs, Q, o, gw, GW, lane);
+      const float res0 = fetch_residual<MB, 2>(a.dx, D, D, Q, gw, lane);
+      stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
+      gemv_phase<MB, 5, 2, false>(w52, L.xwo, L.xbo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
     }
-    prefetch_rows<5, 3>(w53, L.w1, ffn, D, gw, lane);
+    prefetch_rows<5, 3>(w53, L.w1, L.b1, ffn, D, gw, lane);
+    prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln3g, L.ln3b, D);
     bar.sync();
     // ---------------- G: LN3 + fc1 + GELU ----------------
-    stage_x<MB>(xs, red, a.dx, D, D, Q, L.ln3g, L.ln3b);
+    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
-      PhaseOut o{L.b1, 1.f, 0, 1, nullptr, a.dh, ffn, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(w53, L.w1, ffn, D, xs, Q, o, gw, GW, lane);
+      PhaseOut o{1.f, 0, 1, nullptr, a.dh, ffn, nullptr, nullptr, D, a.Tmax, pos};
+      gemv_phase<MB, 5, 3, false>(w53, L.w1, L.b1, ffn, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
     }
+    gsel ^= 1;
     {
       // ---------------- H: fc2 + residual (K = ffn: one row per warp, 20 loads in flight) ----------------
       WR<20, 1> w201;
-      prefetch_rows<20, 1>(w201, L.w2, D, ffn, gw, lane);
+      prefetch_rows<20, 1>(w201, L.w2, L.b2, D, ffn, gw, lane);
       bar.sync();
-      stage_x<MB>(xs, red, a.dh, ffn, ffn, Q, nullptr, nullptr);
-      PhaseOut o{L.b2, 1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 20, 1, false>(w201, L.w2, D, ffn, xs, Q, o, gw, GW, lane);
+      const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
+      stage_x<MB>(xs, a.dh, ffn, ffn, Q, false, mean, rstd);
+      PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
+      gemv_phase<MB, 20, 1, false>(w201, L.w2, L.b2, D, ffn, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
     }
-    if (l + 1 < a.L) prefetch_rows<5, 3>(w53, a.layers[l + 1].wqkv, 3 * D, D, gw, lane);
-    else prefetch_rows<5, 2>(w52, a.embed, a.V, D, gw, lane);
+    if (l + 1 < a.L) {
+      prefetch_rows<5, 3>(w53, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, D, gw, lane);
+      prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[l + 1].ln1g, a.layers[l + 1].ln1b, D);
+    } else {
+      prefetch_rows<5, 2>(w52, a.embed, nullptr, a.V, D, gw, lane);
+      prefetch_gb(gbuf + gsel * 2 * MAXD, a.lnf_g, a.lnf_b, D);
+    }
     bar.sync();
   }
   // ---------------- final LayerNorm + tied LM head ----------------
-  stage_x<MB>(xs, red, a.dx, D, D, Q, a.lnf_g, a.lnf_b);
+  stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
   {
-    PhaseOut o{nullptr, 1.f, 0, 0, nullptr, a.logits, a.V, nullptr, nullptr, D, a.Tmax, pos};
-    gemv_phase<MB, 5, 2, true>(w52, a.embed, a.V, D, xs, Q, o, gw, GW, lane);
+    PhaseOut o{1.f, 0, 0, nullptr, a.logits, a.V, nullptr, nullptr, D, a.Tmax, pos};
+    gemv_phase<MB, 5, 2, true>(w52, a.embed, nullptr, a.V, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
   }
 }
-
-}  // namespace
 
 size_t mega_smem_bytes(int mb, int ffn) {
   const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MAXKEYS + KG * 64) * sizeof(float);
   const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(XKMAX + KG * 64) * sizeof(float);
-  const size_t xs = (size_t)mb * ffn * sizeof(float);
-  const size_t u = xs > attn ? (xs > xattn ? xs : xattn) : (attn > xattn ? attn : xattn);
-  return (MW * 8 + 64) * sizeof(float) + u + 64;
+  return 32 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 4 * MAXD * sizeof(float) + (attn > xattn ? attn : xattn) + 64;
 }
+
+}  // namespace
 
 // Launches the persistent step kernel on `st`.  Returns -3 when the configuration is outside what it supports
 // (the caller then uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   const int Q = a.Q;
-  if (a.L > MEGA_MAXL || Q > 8 || a.D > 1280 || a.ffn > 5120 || a.D % 8 != 0 || a.Tmax > MAXKEYS) return -3;
-  const int mb = Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8));
+  if (a.L > MEGA_MAXL || Q > 2 || a.D > MAXD || a.ffn > 5120 || a.D % 8 != 0 || a.ffn % 8 != 0 || a.Tmax > MAXKEYS) return -3;
+  const int mb = Q <= 1 ? 1 : 2;
   const size_t smem = mega_smem_bytes(mb, a.ffn);
   if (smem > 226 * 1024) return -3;  // 227 KB opt-in limit includes the few bytes of static smem
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
@@ -556,13 +634,10 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   switch (mb) {
     BW_MEGA_CASE(1)
     BW_MEGA_CASE(2)
-    BW_MEGA_CASE(4)
-    BW_MEGA_CASE(8)
   }
 #undef BW_MEGA_CASE
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }
-
 
 }  // namespace bw
