@@ -88,6 +88,7 @@ struct bw_engine {
   bool no_graph = false, simt = false, no_mega = false;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
+  long long* mega_trace = nullptr;
   std::map<std::string, std::pair<void*, size_t>> buffers;
 };
 
@@ -234,6 +235,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
       m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
     }
+    m.trace = e->mega_trace;
     const int rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) mega_done = true;
     else if (rc != -3) return rc;
@@ -498,6 +500,10 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
   if (dalloc(e, "mega_bar", &e->mega_bar, 4)) return -1;
+  {
+    const char* tr = getenv("BW_MEGA_TRACE");
+    if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 2)) return -1;
+  }
   if (dalloc(e, "xcounters", &e->xcounters, (size_t)A * H)) return -1;
   if (dalloc(e, "sup_bits", &e->sup_bits, (size_t)(V + 31) / 32)) return -1;
   if (dalloc(e, "bsup_bits", &e->bsup_bits, (size_t)(V + 31) / 32)) return -1;

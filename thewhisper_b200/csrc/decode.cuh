@@ -86,6 +86,7 @@ struct MegaLayer {
 };
 
 constexpr int MEGA_MAXL = 32;
+constexpr int MEGA_TRACE_N = 264;  // barriers per step that the optional trace records
 
 struct MegaArgs {
   // the per-layer pointer table travels in the kernel parameter block (constant bank, ~8 KB: CUDA >= 12.1 allows 32 KB),
@@ -105,6 +106,7 @@ struct MegaArgs {
   // alignment (word timestamps)
   float* align;
   int Ha, Tcap, step_base;
+  long long* trace;  // optional barrier timeline (debug)
 };
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).

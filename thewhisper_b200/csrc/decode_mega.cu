@@ -57,13 +57,21 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 
 // grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel).  bar.sync orders
 // the CTA's writes before thread 0's release; the acquire poll + bar.sync orders the other CTAs' writes before our reads.
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct GridBar {
   unsigned* ctr;
   unsigned nblocks;
   unsigned epoch;
+  long long* trace;  // optional [nblocks][2*MEGA_TRACE_N]: arrival / release time of every barrier (BW_MEGA_TRACE=1)
   __device__ __forceinline__ void sync() {
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
       ++epoch;
       red_release_add(ctr, 1u);
       const unsigned target = epoch * nblocks;
@@ -76,6 +84,7 @@ struct GridBar {
           }
         }
       }
+      if (trace && epoch <= MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch - 1) * 2 + 1] = global_ns();
     }
     __syncthreads();
   }
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int gw = blockIdx.x * MW + warp, GW = gridDim.x * MW;
   const int D = a.D, H = a.H, Q = a.Q, ffn = a.ffn;
   const int pos = *a.pos;
-  GridBar bar{a.bar, gridDim.x, 0u};
+  GridBar bar{a.bar, gridDim.x, 0u, a.trace};
   float mean[MB], rstd[MB];
   int gsel = 0;  // which gamma/beta buffer the next LN phase uses
 
