@@ -9,7 +9,9 @@
 // The cost model that shaped it (ncu of the first version, profiles/r1_v2_*): 60% of all stall samples were warps parked
 // at the barrier -- a phase is only as fast as its chain of *dependent* L2/DRAM round trips (~0.6-1 us each), not its
 // bytes.  So everything that does not depend on the previous phase is requested BEFORE the barrier that precedes a phase:
-//   * the phase's weight rows (ld.global.nc into registers: all rows of the phase are in flight at once) and bias values,
+//   * the phase's weight rows (cp.async into a per-warp smem slab: all rows of the phase are in flight at once, at no
+//     register cost -- the register-prefetch version spilled them, and every spill store waited for its load, turning
+//     the one round trip into several: 1.4 TB/s effective) and bias values,
 //   * its LayerNorm gamma/beta and the attention K/V rows that are already final (cp.async into smem),
 //   * the barrier itself is one red.release + ld.acquire polling loop (no membar.sc / L1 invalidation; activations that
 //     cross CTAs are read with ld.global.cg),
@@ -34,6 +36,7 @@ constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
 constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
 constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
 constexpr int MAXD = 1280;
+constexpr int ATT_OFF = 32 * 1024;  // attention scratch starts here inside the pool (above the R=1 weight slabs)
 
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
   float2 t;
@@ -90,15 +93,16 @@ struct GridBar {
   }
 };
 
-template <int NC, int R>
-struct WR {
-  uint4 w[R][NC];
+// Per-warp weight slab in shared memory: R rows of K bf16, lane l owns the 16-byte pieces at element offsets l*8 + i*256
+// of each row (it copies them with cp.async and later reads exactly those back, so no CTA sync is needed for the data).
+template <int R>
+struct WB {
   float bias[R];
 };
 
 template <int NC, int R>
-__device__ __forceinline__ void load_rows_m(WR<NC, R>& wr, const bf16* __restrict__ W, const float* __restrict__ bias, int K, int n,
-                                            int N, int lane) {
+__device__ __forceinline__ void slab_load(uint8_t* slab, WB<R>& wb, const bf16* __restrict__ W, const float* __restrict__ bias, int K, int n,
+                                          int N, int lane) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int row = min(n + r, N - 1);
@@ -106,15 +110,16 @@ __device__ __forceinline__ void load_rows_m(WR<NC, R>& wr, const bf16* __restric
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int k = lane * 8 + i * 256;
-      wr.w[r][i] = (k < K) ? ld_nc_u4(wp + k) : make_uint4(0u, 0u, 0u, 0u);
+      if (k < K) cp_async16m(slab + ((size_t)r * K + k) * 2, wp + k);
     }
-    wr.bias[r] = bias ? bias[row] : 0.f;
+    wb.bias[r] = bias ? bias[row] : 0.f;
   }
 }
 
 template <int NC, int R>
-__device__ __forceinline__ void prefetch_rows(WR<NC, R>& w, const bf16* W, const float* bias, int N, int K, int gw, int lane) {
-  if (gw * R < N) load_rows_m<NC, R>(w, W, bias, K, gw * R, N, lane);
+__device__ __forceinline__ void prefetch_rows(uint8_t* pool, WB<R>& wb, const bf16* W, const float* bias, int N, int K, int gw, int warp,
+                                              int lane) {
+  if (gw * R < N) slab_load<NC, R>(pool + (size_t)warp * R * K * 2, wb, W, bias, K, gw * R, N, lane);
 }
 
 // LayerNorm gamma/beta of the NEXT LN phase -> smem (double buffered), requested before the barrier
@@ -176,17 +181,28 @@ __device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src
   }
 }
 
-// rows {gw*R + i*GW*R + r}; `cur` already holds the first pass (prefetched before the preceding barrier)
+// rows {gw*R + i*GW*R + r}; the first pass already sits in this warp's slab (requested before the preceding barrier).
+// PIPE (LM head): two slab sets, the next pass is requested while the current one is consumed.
 template <int MB, int NC, int R, bool PIPE>
-__device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K,
-                                           const float* xs, const float* gb, const float (&mean)[MB], const float (&rstd)[MB], int M,
-                                           const PhaseOut& o, float res0, int gw, int GW, int lane) {
+__device__ __forceinline__ void gemv_phase(uint8_t* pool, WB<R>& wb, const bf16* __restrict__ W, const float* __restrict__ bias, int N,
+                                           int K, const float* xs, const float* gb, const float (&mean)[MB], const float (&rstd)[MB],
+                                           int M, const PhaseOut& o, float res0, int gw, int GW, int warp, int lane) {
+  const size_t slab_bytes = (size_t)R * K * 2;
+  const size_t set_bytes = slab_bytes * MW;
   bool first = true;
+  int buf = 0;
   for (int n = gw * R; n < N; n += GW * R) {
-    WR<NC, R> nxt;  // (dead when !PIPE)
+    const uint8_t* slab = pool + (PIPE ? buf * set_bytes : 0) + (size_t)warp * slab_bytes;
     const int n2 = n + GW * R;
     const bool has_next = n2 < N;
-    if (PIPE && has_next) load_rows_m<NC, R>(nxt, W, bias, K, n2, N, lane);
+    WB<R> nb;
+    if (PIPE) {
+      if (has_next) slab_load<NC, R>(pool + (buf ^ 1) * set_bytes + (size_t)warp * slab_bytes, nb, W, bias, K, n2, N, lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the pass just requested has landed
+    } else if (!first) {
+      cp_async_wait_allm();
+    }
     float acc[R][MB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -196,9 +212,6 @@ __device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restric
     for (int i = 0; i < NC; ++i) {
       const int k = lane * 8 + i * 256;
       if (k < K) {
-        float wf[R][8];
-#pragma unroll
-        for (int r = 0; r < R; ++r) unpack8m(cur.w[r][i], wf[r]);
         float g[8], b[8];
         if (gb) {
           *reinterpret_cast<float4*>(&g[0]) = *reinterpret_cast<const float4*>(gb + k);
@@ -217,9 +230,11 @@ __device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restric
           }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
+            float wf[8];
+            unpack8m(*reinterpret_cast<const uint4*>(slab + ((size_t)r * K + k) * 2), wf);
             float s = acc[r][m];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(wf[r][j], x[j], s);
+            for (int j = 0; j < 8; ++j) s = fmaf(wf[j], x[j], s);
             acc[r][m] = s;
           }
         }
@@ -235,7 +250,7 @@ __device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restric
       float v = 0.f, bv = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (r == r_sel) bv = cur.bias[r];
+        if (r == r_sel) bv = wb.bias[r];
 #pragma unroll
         for (int mm = 0; mm < MB; ++mm)
           if (r == r_sel && mm == m) v = acc[r][mm];
@@ -253,9 +268,14 @@ __device__ __forceinline__ void gemv_phase(WR<NC, R>& cur, const bf16* __restric
     }
     first = false;
     if (PIPE) {
-      if (has_next) cur = nxt;
+      if (has_next) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) wb.bias[r] = nb.bias[r];
+      }
+      buf ^= 1;
     } else if (has_next) {
-      load_rows_m<NC, R>(cur, W, bias, K, n2, N, lane);
+      __syncwarp();
+      slab_load<NC, R>(pool + (size_t)warp * slab_bytes, wb, W, bias, K, n2, N, lane);
     }
   }
 }
@@ -298,7 +318,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   float* red = reinterpret_cast<float*>(dyn);
   float* xs = red + 32;
   float* gbuf = xs + (size_t)MB * a.ffn;
-  uint8_t* att = reinterpret_cast<uint8_t*>(gbuf + 4 * MAXD);
+  uint8_t* pool = reinterpret_cast<uint8_t*>(gbuf + 4 * MAXD);  // weight slabs [0, ...) ; attention scratch from ATT_OFF
+  uint8_t* att = pool + ATT_OFF;  // only R=1 slabs (<= 30 KB) are live while an attention phase runs
   __shared__ unsigned s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -314,9 +335,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // KG key groups x 8 lanes
 
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
-  WR<5, 3> w53;  // QKV and fc1: 3 rows per warp (1776 warps x 3 >= 5120 rows: one pass)
-  WR<5, 2> w52;  // out-proj / cross-q / LM head
-  prefetch_rows<5, 3>(w53, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, lane);
+  WB<3> b3;  // QKV and fc1: 3 rows per warp (1776 warps x 3 >= 5120 rows: one pass)
+  WB<1> b1;  // out-proj / cross-q / fc2: one row per warp
+  WB<2> b2;  // LM head: pipelined row pairs
+  prefetch_rows<5, 3>(pool, b3, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, warp, lane);
   prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[0].ln1g, a.layers[0].ln1b, D);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
@@ -333,10 +355,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dqkv, 3 * D, L.self_k, L.self_v, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(w53, L.wqkv, L.bqkv, 3 * D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
+      gemv_phase<MB, 5, 3, false>(pool, b3, L.wqkv, L.bqkv, 3 * D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
     }
     gsel ^= 1;
-    prefetch_rows<5, 2>(w52, L.wo, L.bo, D, D, gw, lane);
+    __syncthreads();  // every warp is done with its slab: the pool can be re-carved for the next phases
+    prefetch_rows<5, 1>(pool, b1, L.wo, L.bo, D, D, gw, warp, lane);
     // past K/V rows of this CTA's self-attention item do not depend on this step: request them now
     if (blockIdx.x < Q * H) {
       const int q = blockIdx.x / H, h = blockIdx.x - q * H;
@@ -420,22 +443,24 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     bar.sync();
     // ---------------- C: self out-proj + residual ----------------
     {
-      const float res0 = fetch_residual<MB, 2>(a.dx, D, D, Q, gw, lane);
+      const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.wo, L.bo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.wo, L.bo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
     }
-    prefetch_rows<5, 2>(w52, L.xwq, L.xbq, D, D, gw, lane);
+    __syncthreads();
+    prefetch_rows<5, 1>(pool, b1, L.xwq, L.xbq, D, D, gw, warp, lane);
     prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln2g, L.ln2b, D);
     bar.sync();
     // ---------------- D: LN2 + cross q projection ----------------
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dq, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.xwq, L.xbq, D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwq, L.xbq, D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
     }
     gsel ^= 1;
-    prefetch_rows<5, 2>(w52, L.xwo, L.xbo, D, D, gw, lane);
+    __syncthreads();
+    prefetch_rows<5, 1>(pool, b1, L.xwo, L.xbo, D, D, gw, warp, lane);
     // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
     if (blockIdx.x < Q * H * nsplit) {
       const int item = blockIdx.x;
@@ -570,36 +595,38 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     bar.sync();
     // ---------------- F: cross out-proj + residual ----------------
     {
-      const float res0 = fetch_residual<MB, 2>(a.dx, D, D, Q, gw, lane);
+      const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 2, false>(w52, L.xwo, L.xbo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwo, L.xbo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
     }
-    prefetch_rows<5, 3>(w53, L.w1, L.b1, ffn, D, gw, lane);
+    __syncthreads();
+    prefetch_rows<5, 3>(pool, b3, L.w1, L.b1, ffn, D, gw, warp, lane);
     prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln3g, L.ln3b, D);
     bar.sync();
     // ---------------- G: LN3 + fc1 + GELU ----------------
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{1.f, 0, 1, nullptr, a.dh, ffn, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(w53, L.w1, L.b1, ffn, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
+      gemv_phase<MB, 5, 3, false>(pool, b3, L.w1, L.b1, ffn, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
     }
     gsel ^= 1;
     {
       // ---------------- H: fc2 + residual (K = ffn: one row per warp, 20 loads in flight) ----------------
-      WR<20, 1> w201;
-      prefetch_rows<20, 1>(w201, L.w2, L.b2, D, ffn, gw, lane);
+      __syncthreads();
+      prefetch_rows<20, 1>(pool, b1, L.w2, L.b2, D, ffn, gw, warp, lane);
       bar.sync();
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       stage_x<MB>(xs, a.dh, ffn, ffn, Q, false, mean, rstd);
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 20, 1, false>(w201, L.w2, L.b2, D, ffn, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, lane);
+      gemv_phase<MB, 20, 1, false>(pool, b1, L.w2, L.b2, D, ffn, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
     }
+    __syncthreads();
     if (l + 1 < a.L) {
-      prefetch_rows<5, 3>(w53, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, D, gw, lane);
+      prefetch_rows<5, 3>(pool, b3, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, D, gw, warp, lane);
       prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[l + 1].ln1g, a.layers[l + 1].ln1b, D);
     } else {
-      prefetch_rows<5, 2>(w52, a.embed, nullptr, a.V, D, gw, lane);
+      prefetch_rows<5, 2>(pool, b2, a.embed, nullptr, a.V, D, gw, warp, lane);
       prefetch_gb(gbuf + gsel * 2 * MAXD, a.lnf_g, a.lnf_b, D);
     }
     bar.sync();
@@ -608,14 +635,19 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
   {
     PhaseOut o{1.f, 0, 0, nullptr, a.logits, a.V, nullptr, nullptr, D, a.Tmax, pos};
-    gemv_phase<MB, 5, 2, true>(w52, a.embed, nullptr, a.V, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, lane);
+    gemv_phase<MB, 5, 2, true>(pool, b2, a.embed, nullptr, a.V, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
   }
 }
 
 size_t mega_smem_bytes(int mb, int ffn) {
   const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MAXKEYS + KG * 64) * sizeof(float);
   const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(XKMAX + KG * 64) * sizeof(float);
-  return 32 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 4 * MAXD * sizeof(float) + (attn > xattn ? attn : xattn) + 64;
+  const size_t att = ATT_OFF + (attn > xattn ? attn : xattn);
+  const size_t wts = (size_t)MW * 2 * 2 * MAXD * 2 > (size_t)MW * ffn * 2 ? (size_t)MW * 2 * 2 * MAXD * 2 : (size_t)MW * ffn * 2;  // LM head 2 sets of row pairs | fc2 rows
+  const size_t w3 = (size_t)MW * 3 * MAXD * 2;
+  size_t pool = att > wts ? att : wts;
+  if (w3 > pool) pool = w3;
+  return 32 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 4 * MAXD * sizeof(float) + pool + 64;
 }
 
 }  // namespace
