@@ -122,6 +122,39 @@ __device__ __forceinline__ void prefetch_rows(uint8_t* pool, WB<R>& wb, const bf
   if (gw * R < N) slab_load<NC, R>(pool + (size_t)warp * R * K * 2, wb, W, bias, K, gw * R, N, lane);
 }
 
+// DRAM -> L2 prefetch of whole rows, one layer ahead of their use (no register / smem cost).  Measured on the barrier
+// timeline: a slab requested just before its phase's barrier arrives ~5 us later, i.e. the phase stalls 3-4 us on DRAM;
+// with the row already in L2 the cp.async that fills the slab is an L2 hit.
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <int R>
+__device__ __forceinline__ void l2_prefetch_rows(const bf16* W, int N, int K, int gw, int GW, int lane) {
+  if (lane < R) {
+    const int row = gw * R + lane;
+    if (row < N) l2_prefetch(W + (long long)row * K, (uint32_t)K * 2);
+  }
+}
+__device__ __forceinline__ void l2_prefetch_layer(const MegaLayer& L, const MegaArgs& a, int gw, int GW, int lane) {
+  l2_prefetch_rows<3>(L.wqkv, 3 * a.D, a.D, gw, GW, lane);
+  l2_prefetch_rows<1>(L.wo, a.D, a.D, gw, GW, lane);
+  l2_prefetch_rows<1>(L.xwq, a.D, a.D, gw, GW, lane);
+  l2_prefetch_rows<1>(L.xwo, a.D, a.D, gw, GW, lane);
+  l2_prefetch_rows<3>(L.w1, a.ffn, a.D, gw, GW, lane);
+  l2_prefetch_rows<1>(L.w2, a.D, a.ffn, gw, GW, lane);
+  if (threadIdx.x == 0 && blockIdx.x < a.Q * a.H * a.nsplit) {  // this CTA's first cross-attention item
+    const int item = blockIdx.x, nsplit = a.nsplit;
+    const int ks = (a.S + nsplit - 1) / nsplit;
+    const int split = item % nsplit, h = (item / nsplit) % a.H, q = item / (nsplit * a.H);
+    const int s0 = split * ks;
+    const int n = max(0, min(a.S, s0 + ks) - s0);
+    if (n > 0) {
+      l2_prefetch(L.cross_k + (((long long)q * a.H + h) * a.S + s0) * 64, (uint32_t)n * 128);
+      l2_prefetch(L.cross_v + (((long long)q * a.H + h) * a.S + s0) * 64, (uint32_t)n * 128);
+    }
+  }
+}
+
 // LayerNorm gamma/beta of the NEXT LN phase -> smem (double buffered), requested before the barrier
 __device__ __forceinline__ void prefetch_gb(float* gb, const float* __restrict__ g, const float* __restrict__ b, int D) {
   for (int i = threadIdx.x * 4; i < D; i += MT * 4) {
@@ -197,6 +230,10 @@ __device__ __forceinline__ void gemv_phase(uint8_t* pool, WB<R>& wb, const bf16*
     const bool has_next = n2 < N;
     WB<R> nb;
     if (PIPE) {
+      if (lane < R) {  // keep DRAM -> L2 four passes ahead of the slab copies
+        const long long rowp = (long long)n + 4ll * GW * R + lane;
+        if (rowp < N) l2_prefetch(W + rowp * K, (uint32_t)K * 2);
+      }
       if (has_next) slab_load<NC, R>(pool + (buf ^ 1) * set_bytes + (size_t)warp * slab_bytes, nb, W, bias, K, n2, N, lane);
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the pass just requested has landed
@@ -338,6 +375,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   WB<3> b3;  // QKV and fc1: 3 rows per warp (1776 warps x 3 >= 5120 rows: one pass)
   WB<1> b1;  // out-proj / cross-q / fc2: one row per warp
   WB<2> b2;  // LM head: pipelined row pairs
+  l2_prefetch_layer(a.layers[0], a, gw, GW, lane);
   prefetch_rows<5, 3>(pool, b3, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, warp, lane);
   prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[0].ln1g, a.layers[0].ln1b, D);
   if (blockIdx.x == 0) {
@@ -351,6 +389,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
 
   for (int l = 0; l < a.L; ++l) {
     const MegaLayer& L = a.layers[l];
+    if (l + 1 < a.L) l2_prefetch_layer(a.layers[l + 1], a, gw, GW, lane);  // DRAM -> L2, a whole layer ahead
+    else if (lane < 8) {  // first LM-head passes of this warp
+      const long long row = (long long)gw * 2 + (lane & 1) + (long long)(lane >> 1) * GW * 2;
+      if (row < a.V) l2_prefetch(a.embed + row * D, (uint32_t)D * 2);
+    }
     // ---------------- A: LN1 + fused QKV (+ self-KV append) ----------------
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
@@ -562,33 +605,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           a.part_ml[pb * 2 + 0] = mx;
           a.part_ml[pb * 2 + 1] = lsumt;
         }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          const unsigned prev = atomicAdd(&a.xcounters[q * H + h], 1u);
-          s_last = (prev == (unsigned)(nsplit - 1)) ? 1u : 0u;
-        }
-        __syncthreads();
-        if (s_last) {
-          __threadfence();
-          if (threadIdx.x < 64) {
-            const long long hb = ((long long)q * H + h) * nsplit;
-            float M = -INFINITY;
-            for (int sp = 0; sp < nsplit; ++sp)
-              if (__ldcg(&a.part_ml[(hb + sp) * 2 + 1]) > 0.f) M = fmaxf(M, __ldcg(&a.part_ml[(hb + sp) * 2]));
-            float Lsum = 0.f, ov = 0.f;
-            for (int sp = 0; sp < nsplit; ++sp) {
-              const float lv = __ldcg(&a.part_ml[(hb + sp) * 2 + 1]);
-              if (lv > 0.f) {
-                const float w = __expf(__ldcg(&a.part_ml[(hb + sp) * 2]) - M);
-                Lsum = fmaf(lv, w, Lsum);
-                ov = fmaf(__ldcg(&a.part_o[(hb + sp) * 64 + threadIdx.x]), w, ov);
-              }
-            }
-            a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / Lsum;
-          }
-          if (threadIdx.x == 0) a.xcounters[q * H + h] = 0u;
-        }
         __syncthreads();
       }
     }
@@ -596,7 +612,43 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     // ---------------- F: cross out-proj + residual ----------------
     {
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
-      stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      // x = merged cross-attention output: every CTA merges the key-split partials itself (flash-decoding combine;
+      // 3 * nsplit independent L2 loads per element instead of a fence + atomic + last-block chain in phase E)
+      for (int i = threadIdx.x; i < MB * D; i += MT) {
+        const int q = i / D, hd = i - q * D;
+        float v = 0.f;
+        if (q < Q) {
+          const int h = hd >> 6, d = hd & 63;
+          const long long hb = ((long long)q * H + h) * nsplit;
+          float pm[XSPLIT], pl[XSPLIT], po[XSPLIT];
+#pragma unroll
+          for (int sp = 0; sp < XSPLIT; ++sp) {
+            if (sp < nsplit) {
+              pm[sp] = __ldcg(&a.part_ml[(hb + sp) * 2]);
+              pl[sp] = __ldcg(&a.part_ml[(hb + sp) * 2 + 1]);
+              po[sp] = __ldcg(&a.part_o[(hb + sp) * 64 + d]);
+            }
+          }
+          float M = -INFINITY;
+#pragma unroll
+          for (int sp = 0; sp < XSPLIT; ++sp)
+            if (sp < nsplit && pl[sp] > 0.f) M = fmaxf(M, pm[sp]);
+          float Lsum = 0.f, ov = 0.f;
+#pragma unroll
+          for (int sp = 0; sp < XSPLIT; ++sp) {
+            if (sp < nsplit && pl[sp] > 0.f) {
+              const float w = __expf(pm[sp] - M);
+              Lsum = fmaf(pl[sp], w, Lsum);
+              ov = fmaf(po[sp], w, ov);
+            }
+          }
+          v = ov / Lsum;
+        }
+        xs[i] = v;
+      }
+      cp_async_wait_allm();
+      __syncthreads();
+      mean[0] = 0.f;
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
       gemv_phase<MB, 5, 1, false>(pool, b1, L.xwo, L.xbo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
     }
