@@ -236,6 +236,10 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
     }
     m.trace = e->mega_trace;
+    {
+      const char* fl = getenv("BW_MEGA_FLAGS");
+      m.flags = fl ? atoi(fl) : 0;
+    }
     const int rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) mega_done = true;
     else if (rc != -3) return rc;

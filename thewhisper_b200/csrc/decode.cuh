@@ -107,6 +107,7 @@ struct MegaArgs {
   float* align;
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
+  int flags;         // bit0: merge cross-attention splits in the out-proj prologue; bits1-2: L2 prefetch mode (0/1/2)
 };
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).

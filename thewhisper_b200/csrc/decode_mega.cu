@@ -135,6 +135,16 @@ __device__ __forceinline__ void l2_prefetch_rows(const bf16* W, int N, int K, in
     if (row < N) l2_prefetch(W + (long long)row * K, (uint32_t)K * 2);
   }
 }
+// one warp-instruction per 4 KB: lane l prefetches the 128-byte line l of the chunk (plain LSU prefetch, no TMA op)
+__device__ __forceinline__ void l2_line_prefetch_rows(const bf16* W, int N, int K, int R, int gw, int lane) {
+  for (int r = 0; r < R; ++r) {
+    const int row = gw * R + r;
+    if (row >= N) break;
+    const char* base = reinterpret_cast<const char*>(W + (long long)row * K);
+    for (int off = lane * 128; off < K * 2; off += 4096) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off) : "memory");
+  }
+}
+
 __device__ __forceinline__ void l2_prefetch_layer(const MegaLayer& L, const MegaArgs& a, int gw, int GW, int lane) {
   l2_prefetch_rows<3>(L.wqkv, 3 * a.D, a.D, gw, GW, lane);
   l2_prefetch_rows<1>(L.wo, a.D, a.D, gw, GW, lane);
@@ -230,7 +240,7 @@ __device__ __forceinline__ void gemv_phase(uint8_t* pool, WB<R>& wb, const bf16*
     const bool has_next = n2 < N;
     WB<R> nb;
     if (PIPE) {
-      if (lane < R) {  // keep DRAM -> L2 four passes ahead of the slab copies
+      if (false && lane < R) {  // (bulk L2 prefetch ahead of the slab copies: measured slower, TMA issue rate)
         const long long rowp = (long long)n + 4ll * GW * R + lane;
         if (rowp < N) l2_prefetch(W + rowp * K, (uint32_t)K * 2);
       }
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   WB<3> b3;  // QKV and fc1: 3 rows per warp (1776 warps x 3 >= 5120 rows: one pass)
   WB<1> b1;  // out-proj / cross-q / fc2: one row per warp
   WB<2> b2;  // LM head: pipelined row pairs
-  l2_prefetch_layer(a.layers[0], a, gw, GW, lane);
+  if (((a.flags >> 1) & 3) == 1) l2_prefetch_layer(a.layers[0], a, gw, GW, lane);
   prefetch_rows<5, 3>(pool, b3, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, warp, lane);
   prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[0].ln1g, a.layers[0].ln1b, D);
   if (blockIdx.x == 0) {
@@ -389,12 +399,16 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
 
   for (int l = 0; l < a.L; ++l) {
     const MegaLayer& L = a.layers[l];
-    if (l + 1 < a.L) l2_prefetch_layer(a.layers[l + 1], a, gw, GW, lane);  // DRAM -> L2, a whole layer ahead
-    else if (lane < 8) {  // first LM-head passes of this warp
+    const int pfm = (a.flags >> 1) & 3;  // 0 none, 1 bulk prefetch of the whole next layer, 2 per-phase line prefetch
+    if (pfm == 1 && l + 1 < a.L) l2_prefetch_layer(a.layers[l + 1], a, gw, GW, lane);  // DRAM -> L2, a whole layer ahead
+    else if (pfm == 1 && lane < 8) {  // first LM-head passes of this warp
       const long long row = (long long)gw * 2 + (lane & 1) + (long long)(lane >> 1) * GW * 2;
       if (row < a.V) l2_prefetch(a.embed + row * D, (uint32_t)D * 2);
     }
+    const MegaLayer& Ln = a.layers[(l + 1 < a.L) ? l + 1 : l];
+    const bool pf2 = (pfm == 2) && (l + 1 < a.L);
     // ---------------- A: LN1 + fused QKV (+ self-KV append) ----------------
+    if (pf2) l2_line_prefetch_rows(Ln.wqkv, 3 * D, D, 3, gw, lane);
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dqkv, 3 * D, L.self_k, L.self_v, D, a.Tmax, pos};
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     }
     bar.sync();
     // ---------------- C: self out-proj + residual ----------------
+    if (pf2) l2_line_prefetch_rows(Ln.wo, D, D, 1, gw, lane);
     {
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
@@ -496,6 +511,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln2g, L.ln2b, D);
     bar.sync();
     // ---------------- D: LN2 + cross q projection ----------------
+    if (pf2) l2_line_prefetch_rows(Ln.xwq, D, D, 1, gw, lane);
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dq, D, nullptr, nullptr, D, a.Tmax, pos};
@@ -605,15 +621,47 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           a.part_ml[pb * 2 + 0] = mx;
           a.part_ml[pb * 2 + 1] = lsumt;
         }
+        if (!(a.flags & 1)) {  // merge by the last-arriving split of this (sequence, head)
+          __threadfence();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(&a.xcounters[q * H + h], 1u);
+            s_last = (prev == (unsigned)(nsplit - 1)) ? 1u : 0u;
+          }
+          __syncthreads();
+          if (s_last) {
+            __threadfence();
+            if (threadIdx.x < 64) {
+              const long long hb = ((long long)q * H + h) * nsplit;
+              float M = -INFINITY;
+              for (int sp = 0; sp < nsplit; ++sp)
+                if (__ldcg(&a.part_ml[(hb + sp) * 2 + 1]) > 0.f) M = fmaxf(M, __ldcg(&a.part_ml[(hb + sp) * 2]));
+              float Lsum = 0.f, ov = 0.f;
+              for (int sp = 0; sp < nsplit; ++sp) {
+                const float lv = __ldcg(&a.part_ml[(hb + sp) * 2 + 1]);
+                if (lv > 0.f) {
+                  const float w = __expf(__ldcg(&a.part_ml[(hb + sp) * 2]) - M);
+                  Lsum = fmaf(lv, w, Lsum);
+                  ov = fmaf(__ldcg(&a.part_o[(hb + sp) * 64 + threadIdx.x]), w, ov);
+                }
+              }
+              a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / Lsum;
+            }
+            if (threadIdx.x == 0) a.xcounters[q * H + h] = 0u;
+          }
+        }
         __syncthreads();
       }
     }
     bar.sync();
     // ---------------- F: cross out-proj + residual ----------------
+    if (pf2) l2_line_prefetch_rows(Ln.xwo, D, D, 1, gw, lane);
     {
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       // x = merged cross-attention output: every CTA merges the key-split partials itself (flash-decoding combine;
       // 3 * nsplit independent L2 loads per element instead of a fence + atomic + last-block chain in phase E)
+      if (!(a.flags & 1)) stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      else
       for (int i = threadIdx.x; i < MB * D; i += MT) {
         const int q = i / D, hd = i - q * D;
         float v = 0.f;
@@ -657,6 +705,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln3g, L.ln3b, D);
     bar.sync();
     // ---------------- G: LN3 + fc1 + GELU ----------------
+    if (pf2) l2_line_prefetch_rows(Ln.w1, ffn, D, 3, gw, lane);
     stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
     {
       PhaseOut o{1.f, 0, 1, nullptr, a.dh, ffn, nullptr, nullptr, D, a.Tmax, pos};
@@ -668,6 +717,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       __syncthreads();
       prefetch_rows<20, 1>(pool, b1, L.w2, L.b2, D, ffn, gw, warp, lane);
       bar.sync();
+      if (pf2) l2_line_prefetch_rows(Ln.w2, D, ffn, 1, gw, lane);
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       stage_x<MB>(xs, a.dh, ffn, ffn, Q, false, mean, rstd);
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
