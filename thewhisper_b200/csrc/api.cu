@@ -506,7 +506,7 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "mega_bar", &e->mega_bar, 4)) return -1;
   {
     const char* tr = getenv("BW_MEGA_TRACE");
-    if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 2)) return -1;
+    if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 6)) return -1;
   }
   if (dalloc(e, "xcounters", &e->xcounters, (size_t)A * H)) return -1;
   if (dalloc(e, "sup_bits", &e->sup_bits, (size_t)(V + 31) / 32)) return -1;

@@ -165,14 +165,6 @@ __device__ __forceinline__ void l2_prefetch_layer(const MegaLayer& L, const Mega
   }
 }
 
-// LayerNorm gamma/beta of the NEXT LN phase -> smem (double buffered), requested before the barrier
-__device__ __forceinline__ void prefetch_gb(float* gb, const float* __restrict__ g, const float* __restrict__ b, int D) {
-  for (int i = threadIdx.x * 4; i < D; i += MT * 4) {
-    cp_async16m(gb + i, g + i);
-    cp_async16m(gb + MAXD + i, b + i);
-  }
-}
-
 struct PhaseOut {
   float alpha;
   int alpha_cols;
@@ -185,11 +177,25 @@ struct PhaseOut {
   int D, Tmax, pos;
 };
 
-// stage M rows of K floats into smem (ld.global.cg).  With `ln`, every warp then derives mean / rstd of each row on its own
-// (two passes over smem, no block reduction); the normalisation itself happens inside the dot product.
+// LayerNorm gamma/beta slice of this thread (elements [4*tid, 4*tid+4), K <= 4*MT), requested before the barrier
+struct GB {
+  float4 g, b;
+};
+__device__ __forceinline__ void prefetch_gb(GB& gb, const float* __restrict__ g, const float* __restrict__ b, int D) {
+  const int i = threadIdx.x * 4;
+  if (i < D) {
+    gb.g = *reinterpret_cast<const float4*>(g + i);
+    gb.b = *reinterpret_cast<const float4*>(b + i);
+  }
+}
+
+// stage M rows of K floats into smem (ld.global.cg).  With `ln` the rows are LayerNormed in place: every warp derives
+// mean / rstd on its own from the staged row (two passes over smem, no block reduction), then each thread rewrites
+// its 4-element slice.  (Normalising on the fly inside every warp's dot product tripled the smem traffic of a phase;
+// the GEMV phases are bound by the 128 B/clk shared-memory port, not by HBM -- see the barrier timeline in profiles/.)
 template <int MB>
-__device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src, int ld, int K, int M, bool ln, float (&mean)[MB],
-                                        float (&rstd)[MB]) {
+__device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src, int ld, int K, int M, const GB* gb,
+                                        long long* mk = nullptr) {
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x * 4; i < MB * K; i += MT * 4) {
     const int m = i / K, k = i - m * K;
@@ -197,14 +203,13 @@ __device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src
     if (m < M) v = __ldcg(reinterpret_cast<const float4*>(src + (long long)m * ld + k));
     *reinterpret_cast<float4*>(xs + i) = v;
   }
-  cp_async_wait_allm();  // gamma/beta (and anything else this thread prefetched) have landed
+  if (mk && threadIdx.x == 0) mk[0] = global_ns();  // x loads returned
+  cp_async_wait_allm();                             // this thread's slab pieces landed
+  if (mk && threadIdx.x == 0) mk[1] = global_ns();
   __syncthreads();
-#pragma unroll
-  for (int m = 0; m < MB; ++m) {
-    mean[m] = 0.f;
-    rstd[m] = 1.f;
-  }
-  if (!ln) return;
+  if (mk && threadIdx.x == 0) mk[2] = global_ns();  // whole CTA staged
+  if (!gb) return;
+  float mean[MB], rstd[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     float s = 0.f;
@@ -222,14 +227,28 @@ __device__ __forceinline__ void stage_x(float* xs, const float* __restrict__ src
     mean[m] = mu;
     rstd[m] = rsqrtf(warp_sum(ss) / (float)K + 1e-5f);
   }
+  __syncthreads();  // every warp has its statistics before anybody overwrites the raw row
+  const int k = threadIdx.x * 4;
+  if (k < K) {
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      float4 v = *reinterpret_cast<float4*>(xs + m * K + k);
+      v.x = (v.x - mean[m]) * rstd[m] * gb->g.x + gb->b.x;
+      v.y = (v.y - mean[m]) * rstd[m] * gb->g.y + gb->b.y;
+      v.z = (v.z - mean[m]) * rstd[m] * gb->g.z + gb->b.z;
+      v.w = (v.w - mean[m]) * rstd[m] * gb->g.w + gb->b.w;
+      *reinterpret_cast<float4*>(xs + m * K + k) = v;
+    }
+  }
+  __syncthreads();
 }
 
 // rows {gw*R + i*GW*R + r}; the first pass already sits in this warp's slab (requested before the preceding barrier).
 // PIPE (LM head): two slab sets, the next pass is requested while the current one is consumed.
 template <int MB, int NC, int R, bool PIPE>
 __device__ __forceinline__ void gemv_phase(uint8_t* pool, WB<R>& wb, const bf16* __restrict__ W, const float* __restrict__ bias, int N,
-                                           int K, const float* xs, const float* gb, const float (&mean)[MB], const float (&rstd)[MB],
-                                           int M, const PhaseOut& o, float res0, int gw, int GW, int warp, int lane) {
+                                           int K, const float* xs, int M, const PhaseOut& o, float res0, int gw, int GW, int warp,
+                                           int lane) {
   const size_t slab_bytes = (size_t)R * K * 2;
   const size_t set_bytes = slab_bytes * MW;
   bool first = true;
@@ -240,48 +259,42 @@ __device__ __forceinline__ void gemv_phase(uint8_t* pool, WB<R>& wb, const bf16*
     const bool has_next = n2 < N;
     WB<R> nb;
     if (PIPE) {
-      if (false && lane < R) {  // (bulk L2 prefetch ahead of the slab copies: measured slower, TMA issue rate)
-        const long long rowp = (long long)n + 4ll * GW * R + lane;
-        if (rowp < N) l2_prefetch(W + rowp * K, (uint32_t)K * 2);
-      }
       if (has_next) slab_load<NC, R>(pool + (buf ^ 1) * set_bytes + (size_t)warp * slab_bytes, nb, W, bias, K, n2, N, lane);
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the pass just requested has landed
+      __syncwarp();  // lanes read pieces other lanes of the warp copied
     } else if (!first) {
       cp_async_wait_allm();
+      __syncwarp();
     }
     float acc[R][MB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
+    // per 256-element chunk a lane takes elements [4*lane, +4) and [128 + 4*lane, +4): both the fp32 x reads (LDS.128) and
+    // the bf16 weight reads (LDS.64) are contiguous across the warp, i.e. bank-conflict free
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const int k = lane * 8 + i * 256;
-      if (k < K) {
-        float g[8], b[8];
-        if (gb) {
-          *reinterpret_cast<float4*>(&g[0]) = *reinterpret_cast<const float4*>(gb + k);
-          *reinterpret_cast<float4*>(&g[4]) = *reinterpret_cast<const float4*>(gb + k + 4);
-          *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(gb + MAXD + k);
-          *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(gb + MAXD + k + 4);
-        }
+      const int k0 = i * 256 + lane * 4;
+      if (k0 < K) {
+        const bool hi = (k0 + 128) < K;
+        float x0[MB][4], x1[MB][4];
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
-          float x[8];
-          *reinterpret_cast<float4*>(&x[0]) = *reinterpret_cast<const float4*>(&xs[m * K + k]);
-          *reinterpret_cast<float4*>(&x[4]) = *reinterpret_cast<const float4*>(&xs[m * K + k + 4]);
-          if (gb) {
+          *reinterpret_cast<float4*>(x0[m]) = *reinterpret_cast<const float4*>(&xs[m * K + k0]);
+          *reinterpret_cast<float4*>(x1[m]) = hi ? *reinterpret_cast<const float4*>(&xs[m * K + k0 + 128]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (x[j] - mean[m]) * rstd[m] * g[j] + b[j];
-          }
+        for (int r = 0; r < R; ++r) {
+          const uint2 wa = *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0) * 2);
+          const uint2 wc = hi ? *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0 + 128) * 2) : make_uint2(0u, 0u);
+          const float2 a0 = unpack_bf16(wa.x), a1 = unpack_bf16(wa.y), c0 = unpack_bf16(wc.x), c1 = unpack_bf16(wc.y);
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            float wf[8];
-            unpack8m(*reinterpret_cast<const uint4*>(slab + ((size_t)r * K + k) * 2), wf);
+          for (int m = 0; m < MB; ++m) {
             float s = acc[r][m];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(wf[j], x[j], s);
+            s = fmaf(a0.x, x0[m][0], s); s = fmaf(a0.y, x0[m][1], s); s = fmaf(a1.x, x0[m][2], s); s = fmaf(a1.y, x0[m][3], s);
+            s = fmaf(c0.x, x1[m][0], s); s = fmaf(c0.y, x1[m][1], s); s = fmaf(c1.x, x1[m][2], s); s = fmaf(c1.y, x1[m][3], s);
             acc[r][m] = s;
           }
         }
@@ -364,8 +377,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   extern __shared__ __align__(16) uint8_t dyn[];
   float* red = reinterpret_cast<float*>(dyn);
   float* xs = red + 32;
-  float* gbuf = xs + (size_t)MB * a.ffn;
-  uint8_t* pool = reinterpret_cast<uint8_t*>(gbuf + 4 * MAXD);  // weight slabs [0, ...) ; attention scratch from ATT_OFF
+  uint8_t* pool = reinterpret_cast<uint8_t*>(xs + (size_t)MB * a.ffn);  // weight slabs [0, ...) ; attention scratch from ATT_OFF
   uint8_t* att = pool + ATT_OFF;  // only R=1 slabs (<= 30 KB) are live while an attention phase runs
   __shared__ unsigned s_last;
 
@@ -374,8 +386,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int D = a.D, H = a.H, Q = a.Q, ffn = a.ffn;
   const int pos = *a.pos;
   GridBar bar{a.bar, gridDim.x, 0u, a.trace};
-  float mean[MB], rstd[MB];
-  int gsel = 0;  // which gamma/beta buffer the next LN phase uses
+  GB gb;  // gamma/beta slice of the next LayerNorm phase
+  auto marks = [&]() -> long long* {  // 4 marks per barrier epoch, behind the arrive/release table
+    return (a.trace && bar.epoch < MEGA_TRACE_N) ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + ((long long)blockIdx.x * MEGA_TRACE_N + bar.epoch) * 4 : nullptr;
+  };  // which gamma/beta buffer the next LN phase uses
 
   const int nsplit = a.nsplit;
   const int ks = (a.S + nsplit - 1) / nsplit;
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   WB<2> b2;  // LM head: pipelined row pairs
   if (((a.flags >> 1) & 3) == 1) l2_prefetch_layer(a.layers[0], a, gw, GW, lane);
   prefetch_rows<5, 3>(pool, b3, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, D, gw, warp, lane);
-  prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[0].ln1g, a.layers[0].ln1b, D);
+  prefetch_gb(gb, a.layers[0].ln1g, a.layers[0].ln1b, D);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
@@ -406,17 +420,17 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       if (row < a.V) l2_prefetch(a.embed + row * D, (uint32_t)D * 2);
     }
     const MegaLayer& Ln = a.layers[(l + 1 < a.L) ? l + 1 : l];
-    const bool pf2 = (pfm == 2) && (l + 1 < a.L);
+    const bool pf2 = (pfm == 2);  // L2 line prefetch two GEMV phases ahead, issued AFTER this phase's own work
     // ---------------- A: LN1 + fused QKV (+ self-KV append) ----------------
-    if (pf2) l2_line_prefetch_rows(Ln.wqkv, 3 * D, D, 3, gw, lane);
-    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
+    stage_x<MB>(xs, a.dx, D, D, Q, &gb, marks());
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dqkv, 3 * D, L.self_k, L.self_v, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(pool, b3, L.wqkv, L.bqkv, 3 * D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
+      gemv_phase<MB, 5, 3, false>(pool, b3, L.wqkv, L.bqkv, 3 * D, D, xs, Q, o, 0.f, gw, GW, warp, lane);
+      if (a.trace && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) marks()[3] = global_ns();
     }
-    gsel ^= 1;
     __syncthreads();  // every warp is done with its slab: the pool can be re-carved for the next phases
     prefetch_rows<5, 1>(pool, b1, L.wo, L.bo, D, D, gw, warp, lane);
+    if (pf2) l2_line_prefetch_rows(L.xwq, D, D, 1, gw, lane);
     // past K/V rows of this CTA's self-attention item do not depend on this step: request them now
     if (blockIdx.x < Q * H) {
       const int q = blockIdx.x / H, h = blockIdx.x - q * H;
@@ -499,27 +513,28 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     }
     bar.sync();
     // ---------------- C: self out-proj + residual ----------------
-    if (pf2) l2_line_prefetch_rows(Ln.wo, D, D, 1, gw, lane);
     {
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
-      stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      stage_x<MB>(xs, a.dattn, D, D, Q, nullptr, marks());
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 1, false>(pool, b1, L.wo, L.bo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.wo, L.bo, D, D, xs, Q, o, res0, gw, GW, warp, lane);
+      if (a.trace && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) marks()[3] = global_ns();
     }
     __syncthreads();
     prefetch_rows<5, 1>(pool, b1, L.xwq, L.xbq, D, D, gw, warp, lane);
-    prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln2g, L.ln2b, D);
+    if (pf2) l2_line_prefetch_rows(L.xwo, D, D, 1, gw, lane);
+    prefetch_gb(gb, L.ln2g, L.ln2b, D);
     bar.sync();
     // ---------------- D: LN2 + cross q projection ----------------
-    if (pf2) l2_line_prefetch_rows(Ln.xwq, D, D, 1, gw, lane);
-    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
+    stage_x<MB>(xs, a.dx, D, D, Q, &gb, marks());
     {
       PhaseOut o{0.125f, D, 0, nullptr, a.dq, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwq, L.xbq, D, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwq, L.xbq, D, D, xs, Q, o, 0.f, gw, GW, warp, lane);
+      if (a.trace && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) marks()[3] = global_ns();
     }
-    gsel ^= 1;
     __syncthreads();
     prefetch_rows<5, 1>(pool, b1, L.xwo, L.xbo, D, D, gw, warp, lane);
+    if (pf2) l2_line_prefetch_rows(L.w1, ffn, D, 3, gw, lane);
     // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
     if (blockIdx.x < Q * H * nsplit) {
       const int item = blockIdx.x;
@@ -655,12 +670,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     }
     bar.sync();
     // ---------------- F: cross out-proj + residual ----------------
-    if (pf2) l2_line_prefetch_rows(Ln.xwo, D, D, 1, gw, lane);
     {
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
       // x = merged cross-attention output: every CTA merges the key-split partials itself (flash-decoding combine;
       // 3 * nsplit independent L2 loads per element instead of a fence + atomic + last-block chain in phase E)
-      if (!(a.flags & 1)) stage_x<MB>(xs, a.dattn, D, D, Q, false, mean, rstd);
+      if (!(a.flags & 1)) stage_x<MB>(xs, a.dattn, D, D, Q, nullptr);
       else
       for (int i = threadIdx.x; i < MB * D; i += MT) {
         const int q = i / D, hd = i - q * D;
@@ -696,48 +710,49 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       cp_async_wait_allm();
       __syncthreads();
-      mean[0] = 0.f;
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwo, L.xbo, D, D, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
+      gemv_phase<MB, 5, 1, false>(pool, b1, L.xwo, L.xbo, D, D, xs, Q, o, res0, gw, GW, warp, lane);
     }
     __syncthreads();
     prefetch_rows<5, 3>(pool, b3, L.w1, L.b1, ffn, D, gw, warp, lane);
-    prefetch_gb(gbuf + gsel * 2 * MAXD, L.ln3g, L.ln3b, D);
+    if (pf2) l2_line_prefetch_rows(L.w2, D, ffn, 1, gw, lane);
+    prefetch_gb(gb, L.ln3g, L.ln3b, D);
     bar.sync();
     // ---------------- G: LN3 + fc1 + GELU ----------------
-    if (pf2) l2_line_prefetch_rows(Ln.w1, ffn, D, 3, gw, lane);
-    stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
+    stage_x<MB>(xs, a.dx, D, D, Q, &gb, marks());
     {
       PhaseOut o{1.f, 0, 1, nullptr, a.dh, ffn, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 5, 3, false>(pool, b3, L.w1, L.b1, ffn, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
+      gemv_phase<MB, 5, 3, false>(pool, b3, L.w1, L.b1, ffn, D, xs, Q, o, 0.f, gw, GW, warp, lane);
+      if (a.trace && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) marks()[3] = global_ns();
     }
-    gsel ^= 1;
     {
       // ---------------- H: fc2 + residual (K = ffn: one row per warp, 20 loads in flight) ----------------
       __syncthreads();
       prefetch_rows<20, 1>(pool, b1, L.w2, L.b2, D, ffn, gw, warp, lane);
+      if (pf2 && l + 1 < a.L) l2_line_prefetch_rows(Ln.wqkv, 3 * D, D, 3, gw, lane);
       bar.sync();
-      if (pf2) l2_line_prefetch_rows(Ln.w2, D, ffn, 1, gw, lane);
       const float res0 = fetch_residual<MB, 1>(a.dx, D, D, Q, gw, lane);
-      stage_x<MB>(xs, a.dh, ffn, ffn, Q, false, mean, rstd);
+      stage_x<MB>(xs, a.dh, ffn, ffn, Q, nullptr, marks());
       PhaseOut o{1.f, 0, 0, a.dx, a.dx, D, nullptr, nullptr, D, a.Tmax, pos};
-      gemv_phase<MB, 20, 1, false>(pool, b1, L.w2, L.b2, D, ffn, xs, nullptr, mean, rstd, Q, o, res0, gw, GW, warp, lane);
+      gemv_phase<MB, 20, 1, false>(pool, b1, L.w2, L.b2, D, ffn, xs, Q, o, res0, gw, GW, warp, lane);
+      if (a.trace && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) marks()[3] = global_ns();
     }
     __syncthreads();
     if (l + 1 < a.L) {
       prefetch_rows<5, 3>(pool, b3, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, D, gw, warp, lane);
-      prefetch_gb(gbuf + gsel * 2 * MAXD, a.layers[l + 1].ln1g, a.layers[l + 1].ln1b, D);
+      if (pf2) l2_line_prefetch_rows(Ln.wo, D, D, 1, gw, lane);
+      prefetch_gb(gb, a.layers[l + 1].ln1g, a.layers[l + 1].ln1b, D);
     } else {
       prefetch_rows<5, 2>(pool, b2, a.embed, nullptr, a.V, D, gw, warp, lane);
-      prefetch_gb(gbuf + gsel * 2 * MAXD, a.lnf_g, a.lnf_b, D);
+      prefetch_gb(gb, a.lnf_g, a.lnf_b, D);
     }
     bar.sync();
   }
   // ---------------- final LayerNorm + tied LM head ----------------
-  stage_x<MB>(xs, a.dx, D, D, Q, true, mean, rstd);
+  stage_x<MB>(xs, a.dx, D, D, Q, &gb);
   {
     PhaseOut o{1.f, 0, 0, nullptr, a.logits, a.V, nullptr, nullptr, D, a.Tmax, pos};
-    gemv_phase<MB, 5, 2, true>(pool, b2, a.embed, nullptr, a.V, D, xs, gbuf + gsel * 2 * MAXD, mean, rstd, Q, o, 0.f, gw, GW, warp, lane);
+    gemv_phase<MB, 5, 2, true>(pool, b2, a.embed, nullptr, a.V, D, xs, Q, o, 0.f, gw, GW, warp, lane);
   }
 }
 
@@ -749,7 +764,7 @@ size_t mega_smem_bytes(int mb, int ffn) {
   const size_t w3 = (size_t)MW * 3 * MAXD * 2;
   size_t pool = att > wts ? att : wts;
   if (w3 > pool) pool = w3;
-  return 32 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 4 * MAXD * sizeof(float) + pool + 64;
+  return 32 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + pool + 64;
 }
 
 }  // namespace

@@ -2,5 +2,4 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD TRANSFORMERS_OFFLINE=1 HF_HUB_OFFLINE=1 TOKENIZERS_PARALLELISM=false
-for f in 0 1 4 5; do echo "=== flags $f"; BW_MEGA_FLAGS=$f python tools/mega_trace.py 2>&1 | grep -E "step span|work avg|sum slowest"; done 2>&1 | tee gpurun_out/flags.log
-python -m pytest -q -p no:cacheprovider --timeout 300 tests/test_model_gpu.py -k "teacher_forced and mega" 2>&1 | tail -3
+for f in 0 4; do echo "=== flags $f"; BW_MEGA_FLAGS=$f python tools/mega_trace.py 2>&1 | grep -E "step span|work avg|sum slowest"; done 2>&1 | tee gpurun_out/flags.log

@@ -28,7 +28,9 @@ eng.decode_run(40)
 torch.cuda.synchronize()
 N = 264
 nsm = torch.cuda.get_device_properties(0).multi_processor_count
-tr = eng.buffer("mega_trace", torch.int64, (nsm, N, 2)).cpu().numpy()
+raw = eng.buffer("mega_trace", torch.int64, (nsm * N * 6,)).cpu().numpy()
+tr = raw[: nsm * N * 2].reshape(nsm, N, 2)
+mk = raw[nsm * N * 2:].reshape(nsm, N, 4)
 nb = 1 + 8 * dims.dec_layers
 arr, rel = tr[:, :nb, 0], tr[:, :nb, 1]
 t0 = rel[:, 0].min()
@@ -51,3 +53,14 @@ for ph in range(8):
     i = 1 + 8 * l + ph
     a = arr[:, i] - (rel[:, i - 1].min())
     print("layer5", names[i], "arrive offsets us: min %.2f med %.2f max %.2f argmax CTA %d" % (a.min() / 1e3, np.median(a) / 1e3, a.max() / 1e3, a.argmax()))
+
+print("marks relative to the release of the previous barrier (median over CTAs / max), layer 5:")
+for ph, nm in ((0, "A qkv"), (2, "C oproj"), (3, "D xq"), (6, "G fc1"), (7, "H fc2")):
+    i = 1 + 8 * l + ph
+    base = rel[:, i - 1]
+    out = []
+    for j, lab in enumerate(("x loaded", "cp.async landed", "CTA staged", "computed")):
+        d = (mk[:, i, j] - base) / 1e3
+        out.append("%s %.2f/%.2f" % (lab, np.median(d), d.max()))
+    out.append("arrive %.2f/%.2f" % (np.median(arr[:, i] - base) / 1e3, (arr[:, i] - base).max() / 1e3))
+    print("  %-8s %s" % (nm, "  ".join(out)))
