@@ -59,8 +59,9 @@ for ph, nm in ((0, "A qkv"), (2, "C oproj"), (3, "D xq"), (6, "G fc1"), (7, "H f
     i = 1 + 8 * l + ph
     base = rel[:, i - 1]
     out = []
-    for j, lab in enumerate(("x loaded", "cp.async landed", "CTA staged", "computed")):
+    for j, lab in ((2, "x staged"), (0, "last slab landed"), (3, "warp0 done"), (1, "last warp done")):
         d = (mk[:, i, j] - base) / 1e3
+        d = d[mk[:, i, j] > 0]
         out.append("%s %.2f/%.2f" % (lab, np.median(d), d.max()))
     out.append("arrive %.2f/%.2f" % (np.median(arr[:, i] - base) / 1e3, (arr[:, i] - base).max() / 1e3))
     print("  %-8s %s" % (nm, "  ".join(out)))
