@@ -88,11 +88,16 @@ struct GridBar {
   // is live across it (~1 us per phase); (2) the release fence of the arriving thread waits for that thread's OWN outstanding
   // loads -- so the arriving thread is the CTA's last one, which never has a prefetch load in flight (it owns no LayerNorm
   // slice for D <= 1280 and never finishes a row, see prefetch_phase).
-  __device__ __forceinline__ void sync() {
-    __syncthreads();
+  // arrive() right after the CTA's own __syncthreads, wait() after whatever can be requested for the next phase: the arrival
+  // is not delayed by the prefetch issue, and the ~700 read requests of a slab copy queue behind the arrival, not before it
+  __device__ __forceinline__ void arrive() {
     if (threadIdx.x == MT - 1) {
       if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
       red_release_add(ctr, 1u);
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
       if (ld_acquire_u32(ctr) < target) {
         const long long t0 = clock64();
@@ -107,6 +112,11 @@ struct GridBar {
     }
     ++epoch;
     __syncthreads();
+  }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    arrive();
+    wait();
   }
 };
 
@@ -188,18 +198,34 @@ __device__ __forceinline__ void issue_rows(uint8_t* slab, uint64_t* bar, const b
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d, int gw, int lane) {
-  const int n = gw * d.R;
-  if (lane == 0 && n < d.N) {
-    for (int r = 0; r < d.R; ++r)
-      if (n + r < d.N) l2_prefetch(d.W + (long long)(n + r) * d.K, (uint32_t)d.K * 2);
+// The rows of a CTA's 12 warps are contiguous in memory (rows [blockIdx*12*R, +12*R)) and so are their slabs in smem: one
+// TMA operation per CTA and phase.  (Per-row operations cost ~10 ns of TMA issue each -- 36 of them per SM and phase were
+// 0.35 us on the critical path.)
+__device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
+  const int n0 = blockIdx.x * MW * d.R;
+  if (threadIdx.x == 0 && n0 < d.N) {
+    const int rows = min(d.N - n0, MW * d.R);
+    l2_prefetch(d.W + (long long)n0 * d.K, (uint32_t)rows * d.K * 2);
   }
 }
 
-__device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_t* pool, uint64_t* wbar, int gw, int warp, int lane) {
+// What is requested before the barrier that precedes a GEMV phase: the CTA's weight rows (one bulk copy into the slab
+// area, completion on `cbar`), the bias of the row a lane will finish, and this thread's LayerNorm slice.  The LM head
+// (R == 2, many passes) uses per-warp slabs and barriers instead: its passes are refilled warp by warp.
+__device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_t* pool, uint64_t* cbar, uint64_t* wbar, int gw, int warp,
+                                               int lane) {
   const int n = gw * d.R;
+  if (d.R == 2) {
+    if (n < d.N) issue_rows(pool + (size_t)warp * d.R * d.K * 2, wbar, d.W, d.K, d.R, n, d.N, lane);
+  } else {
+    const int n0 = blockIdx.x * MW * d.R;
+    if (threadIdx.x == 0 && n0 < d.N) {
+      const uint32_t bytes = (uint32_t)min(d.N - n0, MW * d.R) * d.K * 2;
+      mbar_arrive_expect_tx(cbar, bytes);
+      bulk_g2s(pool, d.W + (long long)n0 * d.K, bytes, cbar);
+    }
+  }
   if (n < d.N) {
-    issue_rows(pool + (size_t)warp * d.R * d.K * 2, wbar, d.W, d.K, d.R, n, d.N, lane);
     const int r_sel = lane >> 3;
     p.bias = (d.bias && (lane & 7) < 2 && r_sel < d.R && n + r_sel < d.N) ? d.bias[n + r_sel] : 0.f;
   }
@@ -212,16 +238,27 @@ __device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_
 
 // stage M rows of K floats into smem (ld.global.cg), LayerNormed when the phase has one (K <= 4*MT: one float4 per thread
 // and row; two-pass statistics through two block reductions on register-resident values)
-template <int MB>
-__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M) {
+// `between` runs after the x loads were issued and before their values are needed (dead time of one L2 round trip).
+template <int MB, class Between>
+__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, Between&& between) {
   const int K = d.K;
   if (!d.lng) {
-    for (int i = threadIdx.x * 4; i < MB * K; i += MT * 4) {
-      const int m = (MB > 1 && i >= K) ? 1 : 0;
-      const int k = i - m * K;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M) v = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
-      *reinterpret_cast<float4*>(xs + i) = v;
+    constexpr int U = 4;
+    for (int base = threadIdx.x * 4; base < MB * K; base += MT * 4 * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * MT * 4;
+        const int m = (MB > 1 && i >= K) ? 1 : 0;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
+      }
+      if (base == threadIdx.x * 4) between();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * MT * 4;
+        if (i < MB * K) *reinterpret_cast<float4*>(xs + i) = v[u];
+      }
     }
     __syncthreads();
     return;
@@ -235,6 +272,7 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
   }
+  between();
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     const float s = warp_sum((v[m].x + v[m].y) + (v[m].z + v[m].w));
@@ -445,6 +483,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   __shared__ unsigned s_last;
   __shared__ __align__(8) uint64_t wbar[2 * MW];  // per warp: slab barrier (+ second stage for the LM head)
   __shared__ __align__(8) uint64_t xbar;          // cross-attention K/V item
+  __shared__ __align__(8) uint64_t cbar;          // the CTA's weight slabs of a layer phase
   __shared__ long long wts[MW][2];                // trace only: per warp, slab landed / rows finished
   // the per-layer pointer table, copied out of the kernel parameter bank once: dynamically indexed constant loads at every
   // phase boundary missed the constant cache (it shares the 32 KB L1.5 with the instruction stream) -- ~1 us per phase
@@ -463,7 +502,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int nsplit = a.nsplit;
   const int ks = (a.S + nsplit - 1) / nsplit;
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // KG key groups x 8 lanes
-  uint32_t wpar = 0, wpar1 = 0, xpar = 0;                    // mbarrier phase parities
+  uint32_t wpar = 0, wpar1 = 0, xpar = 0, cpar = 0;                    // mbarrier phase parities
 
   {
     static_assert(sizeof(MegaLayer) % 8 == 0, "MegaLayer is copied in 8-byte words");
@@ -474,6 +513,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * MW; ++i) mbar_init(&wbar[i], 1);
     mbar_init(&xbar, 1);
+    mbar_init(&cbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -481,7 +521,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   GemvDesc cur = make_desc(a, sl, 0, 0);
   Pre pre;
-  prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
+  prefetch_phase(cur, pre, pool, &cbar, &wbar[warp], gw, warp, lane);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
@@ -505,12 +545,32 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (cur.residual && active && r_sel < cur.R && m < MB && m < Q && n + r_sel < cur.N)
           res = __ldcg(cur.residual + (long long)m * cur.ldo + n + r_sel);
       }
-      stage_x<MB>(xs, red, cur, pre, Q);
+      auto ahead = [&]() {
+      // two phases ahead, DRAM -> L2 (issued while the x loads of this phase are in flight, when the TMA queue is empty): a
+        // layer is ~54 MB = 8 us of HBM time spread over ~35 us, but a 13 MB slab set requested only one barrier before its
+        // use is still arriving when the phase starts, and the barrier's own atomics queue behind it
+        if (!(a.flags & 1)) {
+          if (ph + 2 <= nph) {
+            const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
+            l2_prefetch_phase(d2);
+          }
+          if (g == 0 && threadIdx.x == 32 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
+            const int item = blockIdx.x;
+            const int split = item % nsplit, h = (item / nsplit) % H, q = item / (nsplit * H);
+            const int s0 = split * ks;
+            const int n = max(0, min(a.S, s0 + ks) - s0);
+            if (n > 0) {
+              l2_prefetch(L.cross_k + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128);
+              l2_prefetch(L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128);
+            }
+          }
+        }
+      };
+      stage_x<MB>(xs, red, cur, pre, Q, ahead);
       mark(2);
       if (mkbase && lane == 0) wts[warp][0] = wts[warp][1] = 0;
       if (active) {
-        mbar_wait(&wbar[warp], wpar);
-        wpar ^= 1u;
+        mbar_wait(&cbar, cpar);
         if (mkbase && lane == 0) wts[warp][0] = global_ns();
         const uint8_t* slab = pool + (size_t)warp * cur.R * cur.K * 2;
         float acc[3][MB];
@@ -520,8 +580,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (mkbase && lane == 0) wts[warp][1] = global_ns();
       }
       mark(3);
+      if (blockIdx.x * MW * cur.R < cur.N) cpar ^= 1u;  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
+    bar.arrive();
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
       long long t0 = 0, t1 = 0;
       for (int w = 0; w < MW; ++w) {
@@ -532,26 +594,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       mkbase[bar.epoch * 4 + 1] = t1;
     }
     cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6);
-    prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
-    // two phases ahead, DRAM -> L2: the slab copies requested above saturate nothing for long (a layer is ~54 MB = 8 us of
-    // HBM time spread over ~35 us), but a 13 MB slab set requested only one barrier before its use is still arriving when
-    // the phase starts and the barrier's own atomics queue behind it
-    if (a.flags & 1) {
-      if (ph + 2 <= nph) {
-        const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
-        l2_prefetch_phase(d2, gw, lane);
-      }
-      if (g == 0 && threadIdx.x == 32 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
-        const int item = blockIdx.x;
-        const int split = item % nsplit, h = (item / nsplit) % H, q = item / (nsplit * H);
-        const int s0 = split * ks;
-        const int n = max(0, min(a.S, s0 + ks) - s0);
-        if (n > 0) {
-          l2_prefetch(L.cross_k + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128);
-          l2_prefetch(L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128);
-        }
-      }
-    }
+    prefetch_phase(cur, pre, pool, &cbar, &wbar[warp], gw, warp, lane);
 
     if (g == 0) {
       // past K/V rows of this CTA's self-attention item do not depend on this step: request them now
@@ -565,7 +608,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
         }
       }
-      bar.sync();
+      bar.wait();
       // ---------------- B: causal self-attention, one (sequence, head) per CTA ----------------
       for (int item = blockIdx.x; item < Q * H; item += gridDim.x) {
         const int q = item / H, h = item - q * H;
@@ -609,7 +652,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           bulk_g2s(att + XKMAX * 128, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
         }
       }
-      bar.sync();
+      bar.wait();
       // ---------------- E: cross-attention, (audio, head, key split) items; last split of a head merges ----------------
       {
         uint8_t* sK = att;
@@ -693,12 +736,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       bar.sync();
     } else {
-      bar.sync();
+      bar.wait();
     }
   }
 
   // ---------------- final LayerNorm + tied LM head: row pairs, two slab stages per warp ----------------
-  stage_x<MB>(xs, red, cur, pre, Q);
+  stage_x<MB>(xs, red, cur, pre, Q, [] {});
   {
     const int K = cur.K, N = cur.N;
     const size_t slab_bytes = (size_t)2 * K * 2;
