@@ -503,7 +503,7 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
-  if (dalloc(e, "mega_bar", &e->mega_bar, 4)) return -1;
+  if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] + per-CTA flags [32, 32 + SMs)
   {
     const char* tr = getenv("BW_MEGA_TRACE");
     if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 6)) return -1;

@@ -96,6 +96,7 @@ struct GridBar {
       red_release_add(ctr, 1u);
     }
   }
+  // (a per-CTA flag array polled by one warp instead of the single counter was tried: 3+ us per barrier)
   __device__ __forceinline__ void wait() {
     if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
@@ -125,6 +126,8 @@ struct GemvDesc {
   const bf16* W;
   const float* bias;
   int N, K, R;            // R rows per warp (1, 2 or 3)
+  int n0, nend;           // rows of this CTA: [n0, nend), contiguous, ceil(N / CTAs) each (the LM head streams: [0, N))
+  bool lm;
   const float* src;       // [M][K] fp32 activations written by an earlier phase
   const float *lng, *lnb; // LayerNorm applied to src while staging (nullptr: none)
   float* out;
@@ -137,6 +140,12 @@ struct GemvDesc {
 };
 
 // g: 0 LN1+QKV | 1 self out-proj | 2 LN2+cross q | 3 cross out-proj | 4 LN3+fc1+GELU | 5 fc2; l == a.L: final LN + LM head
+__device__ __forceinline__ void split_rows(GemvDesc& d) {
+  const int rc = (d.N + (int)gridDim.x - 1) / (int)gridDim.x;
+  d.R = (rc + MW - 1) / MW;
+  d.n0 = min(d.N, (int)blockIdx.x * rc);
+  d.nend = min(d.N, d.n0 + rc);
+}
 __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g) {
   GemvDesc d;
   d.lng = d.lnb = nullptr;
@@ -146,15 +155,15 @@ __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer
   d.alpha_cols = 0;
   d.kc = d.vc = nullptr;
   d.N = d.K = d.ldo = a.D;
-  d.R = 1;
+  d.lm = false;
   if (l >= a.L) {
-    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.src = a.dx; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.V;
+    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.n0 = 0; d.nend = a.V; d.lm = true; d.src = a.dx; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.V;
     return d;
   }
   const MegaLayer& L = layers[l];
   switch (g) {
     case 0:
-      d.W = L.wqkv; d.bias = L.bqkv; d.N = 3 * a.D; d.R = 3; d.src = a.dx; d.lng = L.ln1g; d.lnb = L.ln1b; d.out = a.dqkv; d.ldo = 3 * a.D;
+      d.W = L.wqkv; d.bias = L.bqkv; d.N = 3 * a.D; d.src = a.dx; d.lng = L.ln1g; d.lnb = L.ln1b; d.out = a.dqkv; d.ldo = 3 * a.D;
       d.alpha = 0.125f; d.alpha_cols = a.D; d.kc = L.self_k; d.vc = L.self_v;
       break;
     case 1:
@@ -167,12 +176,13 @@ __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer
       d.W = L.xwo; d.bias = L.xbo; d.src = a.dattn; d.out = a.dx; d.residual = a.dx;
       break;
     case 4:
-      d.W = L.w1; d.bias = L.b1; d.N = a.ffn; d.R = 3; d.src = a.dx; d.lng = L.ln3g; d.lnb = L.ln3b; d.out = a.dh; d.ldo = a.ffn; d.act = 1;
+      d.W = L.w1; d.bias = L.b1; d.N = a.ffn; d.src = a.dx; d.lng = L.ln3g; d.lnb = L.ln3b; d.out = a.dh; d.ldo = a.ffn; d.act = 1;
       break;
     default:
       d.W = L.w2; d.bias = L.b2; d.K = a.ffn; d.src = a.dh; d.out = a.dx; d.residual = a.dx;
       break;
   }
+  split_rows(d);
   return d;
 }
 
@@ -202,11 +212,7 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 // TMA operation per CTA and phase.  (Per-row operations cost ~10 ns of TMA issue each -- 36 of them per SM and phase were
 // 0.35 us on the critical path.)
 __device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
-  const int n0 = blockIdx.x * MW * d.R;
-  if (threadIdx.x == 0 && n0 < d.N) {
-    const int rows = min(d.N - n0, MW * d.R);
-    l2_prefetch(d.W + (long long)n0 * d.K, (uint32_t)rows * d.K * 2);
-  }
+  if (threadIdx.x == 0 && !d.lm && d.n0 < d.nend) l2_prefetch(d.W + (long long)d.n0 * d.K, (uint32_t)(d.nend - d.n0) * d.K * 2);
 }
 
 // What is requested before the barrier that precedes a GEMV phase: the CTA's weight rows (one bulk copy into the slab
@@ -214,21 +220,20 @@ __device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
 // (R == 2, many passes) uses per-warp slabs and barriers instead: its passes are refilled warp by warp.
 __device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_t* pool, uint64_t* cbar, uint64_t* wbar, int gw, int warp,
                                                int lane) {
-  const int n = gw * d.R;
-  if (d.R == 2) {
+  int n;
+  if (d.lm) {
+    n = gw * d.R;
     if (n < d.N) issue_rows(pool + (size_t)warp * d.R * d.K * 2, wbar, d.W, d.K, d.R, n, d.N, lane);
   } else {
-    const int n0 = blockIdx.x * MW * d.R;
-    if (threadIdx.x == 0 && n0 < d.N) {
-      const uint32_t bytes = (uint32_t)min(d.N - n0, MW * d.R) * d.K * 2;
+    n = d.n0 + warp * d.R;
+    if (threadIdx.x == 0 && d.n0 < d.nend) {
+      const uint32_t bytes = (uint32_t)(d.nend - d.n0) * d.K * 2;
       mbar_arrive_expect_tx(cbar, bytes);
-      bulk_g2s(pool, d.W + (long long)n0 * d.K, bytes, cbar);
+      bulk_g2s(pool, d.W + (long long)d.n0 * d.K, bytes, cbar);
     }
   }
-  if (n < d.N) {
-    const int r_sel = lane >> 3;
-    p.bias = (d.bias && (lane & 7) < 2 && r_sel < d.R && n + r_sel < d.N) ? d.bias[n + r_sel] : 0.f;
-  }
+  const int r_sel = lane >> 3;
+  p.bias = (d.bias && (lane & 7) < 2 && r_sel < d.R && n + r_sel < d.nend) ? d.bias[n + r_sel] : 0.f;
   const int k = threadIdx.x * 4;
   if (d.lng && k < d.K) {
     p.g = *reinterpret_cast<const float4*>(d.lng + k);
@@ -316,42 +321,45 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
 // R rows of the warp's slab against the staged x.  Per 256-element chunk a lane takes elements [4*lane, +4) and
 // [128 + 4*lane, +4): both the fp32 x reads (LDS.128) and the bf16 weight reads (LDS.64) are contiguous across the warp.
 template <int MB, int R>
+__device__ __forceinline__ void dot_chunk(const uint8_t* slab, const float* xs, int K, int k0, bool hi, float (&s)[R][MB]) {
+  float4 x0[MB], x1[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    x0[m] = *reinterpret_cast<const float4*>(&xs[m * K + k0]);
+    x1[m] = hi ? *reinterpret_cast<const float4*>(&xs[m * K + k0 + 128]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint2 wa = *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0) * 2);
+    const uint2 wc = hi ? *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0 + 128) * 2) : make_uint2(0u, 0u);
+    const float2 a0 = unpack_bf16(wa.x), a1 = unpack_bf16(wa.y), c0 = unpack_bf16(wc.x), c1 = unpack_bf16(wc.y);
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      float t = s[r][m], u = 0.f;
+      t = fmaf(a0.x, x0[m].x, t); u = fmaf(c0.x, x1[m].x, u);
+      t = fmaf(a0.y, x0[m].y, t); u = fmaf(c0.y, x1[m].y, u);
+      t = fmaf(a1.x, x0[m].z, t); u = fmaf(c1.x, x1[m].z, u);
+      t = fmaf(a1.y, x0[m].w, t); u = fmaf(c1.y, x1[m].w, u);
+      s[r][m] = t + u;
+    }
+  }
+}
+
+// The full 256-element chunks run branch-free (unrolled by 5 so the loads of several chunks are in flight together: with a
+// guard per chunk the compiler serialised load -> convert -> FMA chunk by chunk, ~120 cycles each); a ragged tail
+// (K % 256 != 0: only the small test models) takes the guarded path.
+template <int MB, int R>
 __device__ __forceinline__ void dot_rows(const uint8_t* slab, const float* xs, int K, float (&acc)[3][MB], int lane) {
   float s[R][MB];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int m = 0; m < MB; ++m) s[r][m] = 0.f;
-  for (int kb = 0; kb < K; kb += 5 * 256) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int k0 = kb + i * 256 + lane * 4;
-      if (k0 < K) {
-        const bool hi = (k0 + 128) < K;
-        float4 x0[MB], x1[MB];
-#pragma unroll
-        for (int m = 0; m < MB; ++m) {
-          x0[m] = *reinterpret_cast<const float4*>(&xs[m * K + k0]);
-          x1[m] = hi ? *reinterpret_cast<const float4*>(&xs[m * K + k0 + 128]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint2 wa = *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0) * 2);
-          const uint2 wc = hi ? *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0 + 128) * 2) : make_uint2(0u, 0u);
-          const float2 a0 = unpack_bf16(wa.x), a1 = unpack_bf16(wa.y), c0 = unpack_bf16(wc.x), c1 = unpack_bf16(wc.y);
-#pragma unroll
-          for (int m = 0; m < MB; ++m) {
-            float t = s[r][m], u = 0.f;
-            t = fmaf(a0.x, x0[m].x, t); u = fmaf(c0.x, x1[m].x, u);
-            t = fmaf(a0.y, x0[m].y, t); u = fmaf(c0.y, x1[m].y, u);
-            t = fmaf(a1.x, x0[m].z, t); u = fmaf(c1.x, x1[m].z, u);
-            t = fmaf(a1.y, x0[m].w, t); u = fmaf(c1.y, x1[m].w, u);
-            s[r][m] = t + u;
-          }
-        }
-      }
-    }
-  }
+  const int nfull = K >> 8;
+  int k0 = lane * 4;
+#pragma unroll 5
+  for (int c = 0; c < nfull; ++c, k0 += 256) dot_chunk<MB, R>(slab, xs, K, k0, true, s);
+  if (k0 < K) dot_chunk<MB, R>(slab, xs, K, k0, (k0 + 128) < K, s);
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -364,7 +372,7 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
                                             bool res_valid, int D, int Tmax, int pos, int lane) {
   const int m = lane & 7, r_sel = lane >> 3;
   const int nn = n + r_sel;
-  if (r_sel < d.R && m < MB && m < M && nn < d.N) {
+  if (r_sel < d.R && m < MB && m < M && nn < d.nend) {
     float v = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -537,12 +545,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     const MegaLayer& L = sl[l];
     // ---------------- GEMV phase g of layer l ----------------
     {
-      const int n = gw * cur.R;
-      const bool active = n < cur.N;
+      const int n = cur.n0 + warp * cur.R;
+      const bool active = n < cur.nend;
       float res = 0.f;
       {
         const int m = lane & 7, r_sel = lane >> 3;
-        if (cur.residual && active && r_sel < cur.R && m < MB && m < Q && n + r_sel < cur.N)
+        if (cur.residual && active && r_sel < cur.R && m < MB && m < Q && n + r_sel < cur.nend)
           res = __ldcg(cur.residual + (long long)m * cur.ldo + n + r_sel);
       }
       auto ahead = [&]() {
@@ -575,12 +583,13 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         const uint8_t* slab = pool + (size_t)warp * cur.R * cur.K * 2;
         float acc[3][MB];
         if (cur.R == 3) dot_rows<MB, 3>(slab, xs, cur.K, acc, lane);
+        else if (cur.R == 2) dot_rows<MB, 2>(slab, xs, cur.K, acc, lane);
         else dot_rows<MB, 1>(slab, xs, cur.K, acc, lane);
         finish_rows<MB>(cur, acc, pre.bias, n, Q, res, true, D, a.Tmax, pos, lane);
         if (mkbase && lane == 0) wts[warp][1] = global_ns();
       }
       mark(3);
-      if (blockIdx.x * MW * cur.R < cur.N) cpar ^= 1u;  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
+      if (cur.n0 < cur.nend) cpar ^= 1u;  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
     bar.arrive();
@@ -686,8 +695,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           mbar_wait(&xbar, xpar);
           xpar ^= 1u;
+          mark(0);
           float mx, sum, ov;
           attend_smem(sK, sV, sc, redo, red, qv, n, align_row, mx, sum, ov);
+          mark(1);
           const long long pb = ((long long)q * H + h) * nsplit + split;
           if (threadIdx.x < 64) a.part_o[pb * 64 + threadIdx.x] = ov;
           if (threadIdx.x == 0) {
@@ -702,6 +713,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
             s_last = (prev == (unsigned)(nsplit - 1)) ? 1u : 0u;
           }
           __syncthreads();
+          mark(2);
           if (s_last && threadIdx.x < 64) {
             const long long hb = ((long long)q * H + h) * nsplit;
             float pm[XSPLIT], pl[XSPLIT], po[XSPLIT];
@@ -732,6 +744,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           fence_proxy_async_smem();
           __syncthreads();
+          mark(3);
         }
       }
       bar.sync();
@@ -791,14 +804,18 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   if (a.L > MEGA_MAXL || Q > 2 || a.D > MAXD || a.ffn > 5120 || a.D % 8 != 0 || a.ffn % 8 != 0 || a.Tmax > MAXKEYS) return -3;
   if ((size_t)MW * a.D * 2 > (size_t)ATT_OFF) return -3;  // R=1 slabs must stay below the attention scratch
   const long long GW = (long long)num_sms * MW;
-  if (GW * 3 < 3ll * a.D || GW * 3 < a.ffn || GW < a.D) return -3;  // every layer GEMV is one pass
+  {  // every layer GEMV is one pass of at most 3 rows per warp
+    const int nmax = 3 * a.D > a.ffn ? 3 * a.D : a.ffn;
+    if (((nmax + num_sms - 1) / num_sms + MW - 1) / MW > 3) return -3;
+  }
+  (void)GW;
   if (a.nsplit > XSPLIT) return -3;
   const int mb = Q <= 1 ? 1 : 2;
   const size_t smem = mega_smem_bytes(mb, a.D, a.ffn);
   if (smem + 8 * 1024 > 227 * 1024) return -3;  // the 227 KB opt-in limit includes the static smem (layer table, barriers)
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
-  BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
+  BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
 #define BW_MEGA_CASE(MB)                                                                                              \
   case MB: {                                                                                                          \
     static size_t attr = 0;                                                                                           \

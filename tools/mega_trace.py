@@ -65,3 +65,12 @@ for ph, nm in ((0, "A qkv"), (2, "C oproj"), (3, "D xq"), (6, "G fc1"), (7, "H f
         out.append("%s %.2f/%.2f" % (lab, np.median(d), d.max()))
     out.append("arrive %.2f/%.2f" % (np.median(arr[:, i] - base) / 1e3, (arr[:, i] - base).max() / 1e3))
     print("  %-8s %s" % (nm, "  ".join(out)))
+
+i = 1 + 8 * l + 4
+base = rel[:, i - 1]
+busy = mk[:, i, 0] > 0
+out = []
+for j, lab in enumerate(("K/V + q ready", "attended", "atomic back", "merged")):
+    d = (mk[busy, i, j] - base[busy]) / 1e3
+    out.append("%s %.2f/%.2f" % (lab, np.median(d), d.max()))
+print("  E cross  " + "  ".join(out))
