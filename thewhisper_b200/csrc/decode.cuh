@@ -107,7 +107,8 @@ struct MegaArgs {
   float* align;
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
-  int flags;         // bit0: merge cross-attention splits in the out-proj prologue; bits1-2: L2 prefetch mode (0/1/2)
+  int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments)
+  int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
 };
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).

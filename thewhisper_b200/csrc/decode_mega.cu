@@ -215,22 +215,25 @@ __device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
   if (threadIdx.x == 0 && !d.lm && d.n0 < d.nend) l2_prefetch(d.W + (long long)d.n0 * d.K, (uint32_t)(d.nend - d.n0) * d.K * 2);
 }
 
-// What is requested before the barrier that precedes a GEMV phase: the CTA's weight rows (one bulk copy into the slab
-// area, completion on `cbar`), the bias of the row a lane will finish, and this thread's LayerNorm slice.  The LM head
-// (R == 2, many passes) uses per-warp slabs and barriers instead: its passes are refilled warp by warp.
-__device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_t* pool, uint64_t* cbar, uint64_t* wbar, int gw, int warp,
-                                               int lane) {
+// The CTA's weight rows of a layer phase: one bulk copy into a slab region, completion on that region's mbarrier.
+__device__ __forceinline__ void issue_slabs(const GemvDesc& d, uint8_t* region, uint64_t* cbar) {
+  if (threadIdx.x == 0 && d.n0 < d.nend) {
+    const uint32_t bytes = (uint32_t)(d.nend - d.n0) * d.K * 2;
+    mbar_arrive_expect_tx(cbar, bytes);
+    bulk_g2s(region, d.W + (long long)d.n0 * d.K, bytes, cbar);
+  }
+}
+
+// What is requested before the barrier that precedes a GEMV phase (besides the slabs): the bias of the row a lane will
+// finish and this thread's LayerNorm slice.  The LM head (many passes) uses per-warp slabs and barriers: its passes are
+// refilled warp by warp; its first pass is requested here.
+__device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_t* pool, uint64_t* wbar, int gw, int warp, int lane) {
   int n;
   if (d.lm) {
     n = gw * d.R;
     if (n < d.N) issue_rows(pool + (size_t)warp * d.R * d.K * 2, wbar, d.W, d.K, d.R, n, d.N, lane);
   } else {
     n = d.n0 + warp * d.R;
-    if (threadIdx.x == 0 && d.n0 < d.nend) {
-      const uint32_t bytes = (uint32_t)(d.nend - d.n0) * d.K * 2;
-      mbar_arrive_expect_tx(cbar, bytes);
-      bulk_g2s(pool, d.W + (long long)d.n0 * d.K, bytes, cbar);
-    }
   }
   const int r_sel = lane >> 3;
   p.bias = (d.bias && (lane & 7) < 2 && r_sel < d.R && n + r_sel < d.nend) ? d.bias[n + r_sel] : 0.f;
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   __shared__ unsigned s_last;
   __shared__ __align__(8) uint64_t wbar[2 * MW];  // per warp: slab barrier (+ second stage for the LM head)
   __shared__ __align__(8) uint64_t xbar;          // cross-attention K/V item
-  __shared__ __align__(8) uint64_t cbar;          // the CTA's weight slabs of a layer phase
+  __shared__ __align__(8) uint64_t cbar[2];       // the CTA's weight slabs of a layer phase (one per slab region)
   __shared__ long long wts[MW][2];                // trace only: per warp, slab landed / rows finished
   // the per-layer pointer table, copied out of the kernel parameter bank once: dynamically indexed constant loads at every
   // phase boundary missed the constant cache (it shares the 32 KB L1.5 with the instruction stream) -- ~1 us per phase
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int nsplit = a.nsplit;
   const int ks = (a.S + nsplit - 1) / nsplit;
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;  // KG key groups x 8 lanes
-  uint32_t wpar = 0, wpar1 = 0, xpar = 0, cpar = 0;                    // mbarrier phase parities
+  uint32_t wpar = 0, wpar1 = 0, xpar = 0, cpar0 = 0, cpar1 = 0;                    // mbarrier phase parities
 
   {
     static_assert(sizeof(MegaLayer) % 8 == 0, "MegaLayer is copied in 8-byte words");
@@ -521,7 +524,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * MW; ++i) mbar_init(&wbar[i], 1);
     mbar_init(&xbar, 1);
-    mbar_init(&cbar, 1);
+    mbar_init(&cbar[0], 1);
+    mbar_init(&cbar[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -529,7 +533,14 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   GemvDesc cur = make_desc(a, sl, 0, 0);
   Pre pre;
-  prefetch_phase(cur, pre, pool, &cbar, &wbar[warp], gw, warp, lane);
+  // Slab regions: GEMV phase ph (= 6*layer + g) lives in region ph & 1 -- region 1 at the pool's start (out-proj, cross
+  // out-proj, fc2), region 0 at p0_off (QKV, cross-q, fc1).  Double-buffered (p0_off > 0), the copy for phase ph + 1 is
+  // requested at the START of phase ph: it has landed long before its barrier, which then runs at its ~1.1 us floor (a copy
+  // requested just before the barrier left 0.3-1.3 us of L2 -> smem transfer exposed behind it).  Attention scratch starts
+  // at ATT_OFF, above the small region-1 slabs that are live during the attention phases, and overlays region 0.
+  const bool dbuf = a.p0_off > 0;
+  issue_slabs(cur, pool + a.p0_off, &cbar[0]);
+  prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
@@ -557,6 +568,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       // two phases ahead, DRAM -> L2 (issued while the x loads of this phase are in flight, when the TMA queue is empty): a
         // layer is ~54 MB = 8 us of HBM time spread over ~35 us, but a 13 MB slab set requested only one barrier before its
         // use is still arriving when the phase starts, and the barrier's own atomics queue behind it
+        if (dbuf && ph + 1 < nph) {
+          const GemvDesc d1 = make_desc(a, sl, (ph + 1) / 6, (ph + 1) % 6);
+          issue_slabs(d1, pool + (((ph + 1) & 1) ? 0 : a.p0_off), &cbar[(ph + 1) & 1]);
+        }
         if (!(a.flags & 1)) {
           if (ph + 2 <= nph) {
             const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
@@ -578,9 +593,9 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       mark(2);
       if (mkbase && lane == 0) wts[warp][0] = wts[warp][1] = 0;
       if (active) {
-        mbar_wait(&cbar, cpar);
+        mbar_wait(&cbar[ph & 1], (ph & 1) ? cpar1 : cpar0);
         if (mkbase && lane == 0) wts[warp][0] = global_ns();
-        const uint8_t* slab = pool + (size_t)warp * cur.R * cur.K * 2;
+        const uint8_t* slab = pool + ((ph & 1) ? 0 : a.p0_off) + (size_t)warp * cur.R * cur.K * 2;
         float acc[3][MB];
         if (cur.R == 3) dot_rows<MB, 3>(slab, xs, cur.K, acc, lane);
         else if (cur.R == 2) dot_rows<MB, 2>(slab, xs, cur.K, acc, lane);
@@ -589,7 +604,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (mkbase && lane == 0) wts[warp][1] = global_ns();
       }
       mark(3);
-      if (cur.n0 < cur.nend) cpar ^= 1u;  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
+      if (cur.n0 < cur.nend) {  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
+        if (ph & 1) cpar1 ^= 1u;
+        else cpar0 ^= 1u;
+      }
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
     bar.arrive();
@@ -603,7 +621,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       mkbase[bar.epoch * 4 + 1] = t1;
     }
     cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6);
-    prefetch_phase(cur, pre, pool, &cbar, &wbar[warp], gw, warp, lane);
+    if (!dbuf && !cur.lm) issue_slabs(cur, pool, &cbar[(ph + 1) & 1]);
+    prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
 
     if (g == 0) {
       // past K/V rows of this CTA's self-attention item do not depend on this step: request them now
@@ -781,18 +800,33 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   }
 }
 
-size_t mega_smem_bytes(int mb, int D, int ffn) {
+// smem plan: returns the dynamic smem bytes and the offset of slab region 0 (0: single-buffered, everything at the pool's start)
+size_t mega_smem_plan(int mb, int D, int ffn, int num_sms, bool want_dbuf, int* p0_off) {
+  // rows of a CTA, rounded up to whole active warps: the unused rows of the last active warp are still read (and discarded)
+  auto rc = [&](int n) {
+    const int rows = (n + num_sms - 1) / num_sms, R = (rows + MW - 1) / MW;
+    return (size_t)((rows + R - 1) / R * R);
+  };
   const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MAXKEYS + MW * 64) * sizeof(float);
   const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(XKMAX + MW * 64) * sizeof(float);
   const size_t att = ATT_OFF + (attn > xattn ? attn : xattn);
-  const size_t lm = (size_t)MW * 2 * 2 * D * 2;  // LM head: 2 stages of row pairs
-  const size_t w2 = (size_t)MW * ffn * 2;        // fc2: one row of K = ffn per warp
-  const size_t w3 = (size_t)MW * 3 * D * 2;      // QKV / fc1: three rows per warp
-  size_t pool = att;
-  if (lm > pool) pool = lm;
-  if (w2 > pool) pool = w2;
-  if (w3 > pool) pool = w3;
-  return 64 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + pool + 128;
+  const size_t lm = (size_t)MW * 2 * 2 * D * 2;  // LM head: 2 stages of row pairs per warp
+  size_t r1 = rc(D) * ffn * 2;                   // region 1: out-proj / cross out-proj (K = D), fc2 (K = ffn)
+  if (rc(D) * D * 2 > r1) r1 = rc(D) * D * 2;
+  size_t r0 = rc(3 * D) * D * 2;                 // region 0: QKV, cross-q, fc1
+  if (rc(ffn) * D * 2 > r0) r0 = rc(ffn) * D * 2;
+  if (rc(D) * D * 2 > r0) r0 = rc(D) * D * 2;
+  const size_t fixed = 64 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 128;
+  const size_t limit = 227 * 1024 - 8 * 1024;   // the opt-in limit includes the static smem (layer table, barriers)
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  const size_t off = (r1 + 127) / 128 * 128;
+  const size_t pool_d = mx(mx(off + r0, att), lm);
+  if (want_dbuf && fixed + pool_d <= limit) {
+    *p0_off = (int)off;
+    return fixed + pool_d;
+  }
+  *p0_off = 0;
+  return fixed + mx(mx(mx(r0, r1), att), lm);
 }
 
 }  // namespace
@@ -811,8 +845,10 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   (void)GW;
   if (a.nsplit > XSPLIT) return -3;
   const int mb = Q <= 1 ? 1 : 2;
-  const size_t smem = mega_smem_bytes(mb, a.D, a.ffn);
+  MegaArgs b = a;
+  const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
   if (smem + 8 * 1024 > 227 * 1024) return -3;  // the 227 KB opt-in limit includes the static smem (layer table, barriers)
+  if ((size_t)((a.D + num_sms - 1) / num_sms) * a.D * 2 > (size_t)ATT_OFF) return -3;  // region-1 slabs live under the attention scratch
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
@@ -823,7 +859,7 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
       BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = smem;                                                                                                    \
     }                                                                                                                 \
-    decode_mega_kernel<MB><<<num_sms, MT, smem, st>>>(a);                                                             \
+    decode_mega_kernel<MB><<<num_sms, MT, smem, st>>>(b);                                                             \
   } break;
   switch (mb) {
     BW_MEGA_CASE(1)
