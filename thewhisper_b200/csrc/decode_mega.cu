@@ -35,6 +35,7 @@ namespace {
 
 constexpr int MT = 384;        // threads per CTA (12 warps: <= 170 registers per thread)
 constexpr int MW = MT / 32;    // warps per CTA
+constexpr int DMA_T = MT - 32;  // first lane of the last warp: issues every TMA operation (it takes no part in x staging)
 constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
 constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
 constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
@@ -212,12 +213,12 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 // TMA operation per CTA and phase.  (Per-row operations cost ~10 ns of TMA issue each -- 36 of them per SM and phase were
 // 0.35 us on the critical path.)
 __device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
-  if (threadIdx.x == 0 && !d.lm && d.n0 < d.nend) l2_prefetch(d.W + (long long)d.n0 * d.K, (uint32_t)(d.nend - d.n0) * d.K * 2);
+  if (threadIdx.x == DMA_T && !d.lm && d.n0 < d.nend) l2_prefetch(d.W + (long long)d.n0 * d.K, (uint32_t)(d.nend - d.n0) * d.K * 2);
 }
 
 // The CTA's weight rows of a layer phase: one bulk copy into a slab region, completion on that region's mbarrier.
 __device__ __forceinline__ void issue_slabs(const GemvDesc& d, uint8_t* region, uint64_t* cbar) {
-  if (threadIdx.x == 0 && d.n0 < d.nend) {
+  if (threadIdx.x == DMA_T && d.n0 < d.nend) {
     const uint32_t bytes = (uint32_t)(d.nend - d.n0) * d.K * 2;
     mbar_arrive_expect_tx(cbar, bytes);
     bulk_g2s(region, d.W + (long long)d.n0 * d.K, bytes, cbar);
@@ -244,34 +245,42 @@ __device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_
   }
 }
 
-// stage M rows of K floats into smem (ld.global.cg), LayerNormed when the phase has one (K <= 4*MT: one float4 per thread
-// and row; two-pass statistics through two block reductions on register-resident values)
-// `between` runs after the x loads were issued and before their values are needed (dead time of one L2 round trip).
-template <int MB, class Between>
-__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, Between&& between) {
+// stage M rows of K floats into smem (ld.global.cg), LayerNormed when the phase has one.
+// The last warp takes no part in the staging: it runs `dma` (the TMA requests of the coming phases, ~0.25 us of issue
+// time) meanwhile and only joins the final CTA barrier.  The staging warps synchronise among themselves on named barrier 1.
+__device__ __forceinline__ void stage_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MT - 32) : "memory"); }
+
+template <int MB, class Dma>
+__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, Dma&& dma) {
   const int K = d.K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == MW - 1) {
+    dma();
+    __syncthreads();
+    return;
+  }
+  constexpr int ST = MT - 32;  // staging threads
   if (!d.lng) {
     constexpr int U = 4;
-    for (int base = threadIdx.x * 4; base < MB * K; base += MT * 4 * U) {
+    for (int base = threadIdx.x * 4; base < MB * K; base += ST * 4 * U) {
       float4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * MT * 4;
+        const int i = base + u * ST * 4;
         const int m = (MB > 1 && i >= K) ? 1 : 0;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
       }
-      if (base == threadIdx.x * 4) between();
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * MT * 4;
+        const int i = base + u * ST * 4;
         if (i < MB * K) *reinterpret_cast<float4*>(xs + i) = v[u];
       }
     }
     __syncthreads();
     return;
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // LayerNorm (K <= 4 * ST): one float4 per thread and row, two-pass statistics through two reductions on register values
   const int k = threadIdx.x * 4;
   const bool have = k < K;
   float4 v[MB];
@@ -280,19 +289,18 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
   }
-  between();
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     const float s = warp_sum((v[m].x + v[m].y) + (v[m].z + v[m].w));
     if (lane == 0) red[m * MW + warp] = s;
   }
-  __syncthreads();
+  stage_sync();
   float mean[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < MW; ++w) s += red[m * MW + w];
+    for (int w = 0; w < MW - 1; ++w) s += red[m * MW + w];
     mean[m] = s / (float)K;
     float ss = 0.f;
     if (have) {
@@ -302,12 +310,12 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     ss = warp_sum(ss);
     if (lane == 0) red[(MB + m) * MW + warp] = ss;
   }
-  __syncthreads();
+  stage_sync();
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     float ss = 0.f;
 #pragma unroll
-    for (int w = 0; w < MW; ++w) ss += red[(MB + m) * MW + w];
+    for (int w = 0; w < MW - 1; ++w) ss += red[(MB + m) * MW + w];
     const float rstd = rsqrtf(ss / (float)K + 1e-5f);
     if (have) {
       float4 o;
@@ -321,8 +329,6 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   __syncthreads();
 }
 
-// R rows of the warp's slab against the staged x.  Per 256-element chunk a lane takes elements [4*lane, +4) and
-// [128 + 4*lane, +4): both the fp32 x reads (LDS.128) and the bf16 weight reads (LDS.64) are contiguous across the warp.
 template <int MB, int R>
 __device__ __forceinline__ void dot_chunk(const uint8_t* slab, const float* xs, int K, int k0, bool hi, float (&s)[R][MB]) {
   float4 x0[MB], x1[MB];
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
             const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
             l2_prefetch_phase(d2);
           }
-          if (g == 0 && threadIdx.x == 32 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
+          if (g == 0 && threadIdx.x == DMA_T + 1 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
             const int item = blockIdx.x;
             const int split = item % nsplit, h = (item / nsplit) % H, q = item / (nsplit * H);
             const int s0 = split * ks;
