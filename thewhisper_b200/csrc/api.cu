@@ -73,7 +73,8 @@ struct bw_engine {
   bf16 *self_k = nullptr, *self_v = nullptr;    // [L][Q][Tmax][D]
   // decoder state
   int *tokens = nullptr, *finished = nullptr, *pos = nullptr, *anc = nullptr, *anc_tmp = nullptr, *head_slots = nullptr;
-  unsigned *done_ctr = nullptr, *xcounters = nullptr, *sup_bits = nullptr, *bsup_bits = nullptr;
+  unsigned *done_ctr = nullptr, *xcounters = nullptr, *sup_bits = nullptr, *bsup_bits = nullptr, *sel_ctr = nullptr;
+  unsigned long long* sel_best = nullptr;
   float *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dq = nullptr, *dh = nullptr, *logits = nullptr, *part_o = nullptr,
         *part_ml = nullptr, *align = nullptr, *lse = nullptr, *ts_work = nullptr, *ts_out = nullptr;
   int *reorder_tmp = nullptr, *cand_tokens = nullptr;
@@ -208,7 +209,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
   const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, V = e->V, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
   const long long self_layer0 = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
   const long long cross_layer0 = (long long)e->cfg.max_audios * H * S * 64;
-  bool mega_done = false;
+  bool mega_done = false, select_done = false;
   if (!e->no_mega && G == 1 && Q <= 8 && (int)e->dec.size() <= MEGA_MAXL) {
     // persistent one-kernel step (decode_mega.cu); falls through to the per-op path when unsupported (-3)
     MegaArgs m{};
@@ -236,12 +237,21 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
     }
     m.trace = e->mega_trace;
+    if (!e->opts.timestamp_rules && !getenv("BW_NO_FUSED_SELECT")) {
+      m.fuse_select = 1;
+      m.suppress_bits = e->sup_bits; m.begin_suppress_bits = e->bsup_bits; m.begin_index = e->opts.begin_index;
+      m.eos = e->opts.eos_token; m.pad = e->opts.pad_token; m.finished = e->finished; m.tokens_rw = e->tokens; m.pos_rw = e->pos;
+      m.sel_best = e->sel_best; m.sel_ctr = e->sel_ctr;
+    }
     {
       const char* fl = getenv("BW_MEGA_FLAGS");
       m.flags = fl ? atoi(fl) : 0;
     }
     const int rc = launch_decode_mega(st, m, e->num_sms);
-    if (rc == 0) mega_done = true;
+    if (rc == 0) {
+      mega_done = true;
+      select_done = m.fuse_select != 0;
+    }
     else if (rc != -3) return rc;
   }
   if (!mega_done) {
@@ -332,6 +342,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     if (int rc = launch_gemv(st, g)) return rc;
   }
   }  // !mega_done
+  if (select_done) return 0;
   SelectArgs s;
   s.logits = e->logits; s.V = V; s.Q = Q; s.Tmax = Tmax; s.tokens = e->tokens; s.finished = e->finished; s.pos = e->pos;
   s.done_ctr = e->done_ctr; s.suppress_bits = e->sup_bits; s.begin_suppress_bits = e->bsup_bits;
@@ -509,6 +520,8 @@ int bw_engine_finalize(bw_engine* e) {
     if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 6)) return -1;
   }
   if (dalloc(e, "xcounters", &e->xcounters, (size_t)A * H)) return -1;
+  if (dalloc(e, "sel_ctr", &e->sel_ctr, 1)) return -1;
+  if (dalloc(e, "sel_best", &e->sel_best, (size_t)Qm)) return -1;
   if (dalloc(e, "sup_bits", &e->sup_bits, (size_t)(V + 31) / 32)) return -1;
   if (dalloc(e, "bsup_bits", &e->bsup_bits, (size_t)(V + 31) / 32)) return -1;
   if (dalloc(e, "dx", &e->dx, (size_t)Qm * D)) return -1;

@@ -108,6 +108,17 @@ struct MegaArgs {
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
   int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments)
+  // greedy token selection fused behind the LM head (no timestamp rules, one beam): masked arg-max by 64-bit atomicMax,
+  // the last CTA to finish writes the token, handles EOS / pad and advances the position -- no select kernel
+  int fuse_select;
+  const unsigned* suppress_bits;
+  const unsigned* begin_suppress_bits;
+  int begin_index, eos, pad;
+  int* finished;
+  int* tokens_rw;
+  int* pos_rw;
+  unsigned long long* sel_best;  // [Q], zero between steps
+  unsigned* sel_ctr;             // zero between steps
   int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
 };
 

@@ -402,90 +402,109 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
   }
 }
 
-__device__ __forceinline__ float block_max_m(float v, float* red) {
-  v = warp_max(v);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float r = red[0];
-#pragma unroll
-  for (int w = 1; w < MW; ++w) r = fmaxf(r, red[w]);
-  __syncthreads();
-  return r;
-}
-__device__ __forceinline__ float block_sum_m(float v, float* red) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float r = 0.f;
-#pragma unroll
-  for (int w = 0; w < MW; ++w) r += red[w];
-  __syncthreads();
-  return r;
-}
-
-// scores, softmax numerators and the un-normalised P.V of one work item whose n keys sit in smem (sK / sV rows of 128 B).
-// Returns (max, sum) and leaves the 64 output sums in out64[0..64) (valid for threads < 64 after the call).
-__device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV, float* sc, float* redo, float* red, const float (&qv)[8],
-                                            int n, float* score_out, float& mx_out, float& sum_out, float& ov_out) {
+// Scores, softmax numerators and the un-normalised P.V of one work item whose n <= NJ*KG keys sit in smem (rows of 128 B).
+// Key group g (8 lanes, 8 dims each) owns keys g, g + KG, ...: its scores stay in registers, all smem reads of a pass are
+// issued together (fully unrolled, predicated), and there are two CTA barriers in all: one for the maximum, one for the
+// final fold of (sum, 64 outputs) across warps.  Returns max / sum / (threads < 64) the output sums.
+// red: [2][MW] floats, redo: [MW][64 + 8] floats.
+template <int NJ>
+__device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV, float* redo, float* red, const float (&qv)[8], int n,
+                                            float* score_out, float& mx_out, float& sum_out, float& ov_out, long long* mk = nullptr) {
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  float lmax = -INFINITY;
-  for (int kb = 0; kb < n; kb += KG) {
-    const int kk = kb + grp;
-    float d = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // separate passes so that the NJ independent chains overlap: loads + FMAs of all keys, then the three shuffle stages
+  // across all keys (one dependent shuffle chain per key cost ~150 cycles per key when interleaved with the FMAs)
+  float d[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int kk = grp + j * KG;
+    float t0 = 0.f, t1 = 0.f;
     if (kk < n) {
       float kf[8];
       unpack8m(*reinterpret_cast<const uint4*>(sK + kk * 128 + sub * 16), kf);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d = fmaf(qv[j], kf[j], d);
-    }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 4);
-    if (kk < n) {
-      if (sub == 0) {
-        sc[kk] = d;
-        if (score_out) score_out[kk] = d;
+      for (int i = 0; i < 4; ++i) {
+        t0 = fmaf(qv[i], kf[i], t0);
+        t1 = fmaf(qv[i + 4], kf[i + 4], t1);
       }
-      lmax = fmaxf(lmax, d);
+    }
+    d[j] = t0 + t1;
+  }
+#pragma unroll
+  for (int st = 1; st < 8; st <<= 1) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], st);
+  }
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int kk = grp + j * KG;
+    if (kk < n) {
+      lmax = fmaxf(lmax, d[j]);
+      if (score_out && sub == 0) score_out[kk] = d[j];
     }
   }
-  const float mx = block_max_m(lmax, red);
-  float lsum = 0.f;
-  for (int kk = threadIdx.x; kk < n; kk += MT) {
-    const float e = __expf(sc[kk] - mx);
-    sc[kk] = e;
-    lsum += e;
-  }
-  const float lsumt = block_sum_m(lsum, red);
-  float acc[8];
+  lmax = warp_max(lmax);
+  if (mk && threadIdx.x == 0) { mk[1] = global_ns(); mk[3] = clock64(); }
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  float mx = red[0];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int kk = grp; kk < n; kk += KG) {
-    float vf[8];
-    unpack8m(*reinterpret_cast<const uint4*>(sV + kk * 128 + sub * 16), vf);
-    const float p = sc[kk];
+  for (int w = 1; w < MW; ++w) mx = fmaxf(mx, red[w]);
+  float acc[8], lsum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
-  }
-  // fold the 4 key groups of a warp with shuffles (lanes with equal sub), then 12 warp partials through smem
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  {  // one exp per key (not one per lane): lane (j & 7) of the group exponentiates key j, the group shares it by shuffle
+    float mine = 0.f, mine2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    for (int j = 0; j < NJ; ++j)
+      if ((j & 7) == sub) {
+        if (j < 8) mine = d[j];
+        else mine2 = d[j];
+      }
+    mine = __expf(mine - mx);
+    if (NJ > 8) mine2 = __expf(mine2 - mx);
+    const int gl = lane & 24;  // first lane of this group of 8
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float e = __shfl_sync(0xffffffffu, j < 8 ? mine : mine2, gl + (j & 7));
+      d[j] = (grp + j * KG < n) ? e : 0.f;
+    }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int kk = grp + j * KG;
+    if (kk < n) {
+      lsum += d[j];
+      float vf[8];
+      unpack8m(*reinterpret_cast<const uint4*>(sV + kk * 128 + sub * 16), vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(d[j], vf[i], acc[i]);
+    }
+  }
+  // fold the 4 key groups of a warp with shuffles (lanes with equal sub), then the 12 warp partials through smem
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);  // (all 8 lanes of a group hold the same sum)
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
   if (lane < 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) redo[warp * 64 + lane * 8 + j] = acc[j];
+    for (int i = 0; i < 8; ++i) redo[warp * 72 + lane * 8 + i] = acc[i];
+    if (lane == 0) redo[warp * 72 + 64] = lsum;
   }
   __syncthreads();
-  float ov = 0.f;
+  float ov = 0.f, ls = 0.f;
+#pragma unroll
+  for (int w = 0; w < MW; ++w) ls += redo[w * 72 + 64];
   if (threadIdx.x < 64) {
 #pragma unroll
-    for (int w = 0; w < MW; ++w) ov += redo[w * 64 + threadIdx.x];
+    for (int w = 0; w < MW; ++w) ov += redo[w * 72 + threadIdx.x];
   }
   mx_out = mx;
-  sum_out = lsumt;
+  sum_out = ls;
   ov_out = ov;
 }
 
@@ -649,8 +668,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         const int n = pos + 1;
         uint8_t* sK = att;
         uint8_t* sV = att + (size_t)MAXKEYS * 128;
-        float* sc = reinterpret_cast<float*>(att + (size_t)MAXKEYS * 256);
-        float* redo = sc + MAXKEYS;  // [MW][64]
+        float* redo = reinterpret_cast<float*>(att + (size_t)MAXKEYS * 256);  // [MW][72]
         const int s_first = (item == blockIdx.x) ? pos : 0;  // rows < pos of the first item were prefetched
         for (int s = s_first + grp; s < n; s += KG) {
           const long long off = ((long long)q * a.Tmax + s) * D + h * 64 + sub * 8;
@@ -666,7 +684,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         cp_async_wait_allm();
         __syncthreads();  // the row of position `pos` was copied by group 0, whatever group reads it below
         float mx, sum, ov;
-        attend_smem(sK, sV, sc, redo, red, qv, n, nullptr, mx, sum, ov);
+        if (n <= 3 * KG) attend_smem<3>(sK, sV, redo, red, qv, n, nullptr, mx, sum, ov);
+        else attend_smem<(MAXKEYS + KG - 1) / KG>(sK, sV, redo, red, qv, n, nullptr, mx, sum, ov);
         if (threadIdx.x < 64) a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / sum;
         fence_proxy_async_smem();  // this thread's scratch writes (generic proxy) before later TMA writes to the same bytes
         __syncthreads();
@@ -691,8 +710,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       {
         uint8_t* sK = att;
         uint8_t* sV = att + XKMAX * 128;
-        float* sc = reinterpret_cast<float*>(att + 2 * XKMAX * 128);
-        float* redo = sc + XKMAX;  // [MW][64]
+        float* redo = reinterpret_cast<float*>(att + 2 * XKMAX * 128);  // [MW][72]
         for (int item = blockIdx.x; item < Q * H * nsplit; item += gridDim.x) {
           const int split = item % nsplit;
           const int h = (item / nsplit) % H;
@@ -721,9 +739,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           mbar_wait(&xbar, xpar);
           xpar ^= 1u;
           mark(0);
+          if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) mkbase[bar.epoch * 4 + 2] = clock64();
           float mx, sum, ov;
-          attend_smem(sK, sV, sc, redo, red, qv, n, align_row, mx, sum, ov);
-          mark(1);
+          attend_smem<(XKMAX + KG - 1) / KG>(sK, sV, redo, red, qv, n, align_row, mx, sum, ov,
+                                             (mkbase && bar.epoch < MEGA_TRACE_N) ? mkbase + bar.epoch * 4 : nullptr);
           const long long pb = ((long long)q * H + h) * nsplit + split;
           if (threadIdx.x < 64) a.part_o[pb * 64 + threadIdx.x] = ov;
           if (threadIdx.x == 0) {
@@ -738,7 +757,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
             s_last = (prev == (unsigned)(nsplit - 1)) ? 1u : 0u;
           }
           __syncthreads();
-          mark(2);
           if (s_last && threadIdx.x < 64) {
             const long long hb = ((long long)q * H + h) * nsplit;
             float pm[XSPLIT], pl[XSPLIT], po[XSPLIT];
@@ -769,7 +787,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           fence_proxy_async_smem();
           __syncthreads();
-          mark(3);
         }
       }
       bar.sync();
@@ -780,11 +797,13 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
 
   // ---------------- final LayerNorm + tied LM head: row pairs, two slab stages per warp ----------------
   stage_x<MB>(xs, red, cur, pre, Q, [] {});
+  unsigned long long best = 0ull;  // of the logits this lane finished: (order-preserving value bits << 32) | ~token
   {
     const int K = cur.K, N = cur.N;
     const size_t slab_bytes = (size_t)2 * K * 2;
     const size_t set_bytes = slab_bytes * MW;
     int buf = 0;
+    const bool at_begin = (pos + 1 == a.begin_index) && a.begin_suppress_bits;
     for (int n = gw * 2; n < N; n += GW * 2) {
       const int n2 = n + GW * 2;
       if (n2 < N) {
@@ -801,8 +820,67 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       float acc[3][MB];
       dot_rows<MB, 2>(pool + buf * set_bytes + (size_t)warp * slab_bytes, xs, K, acc, lane);
       finish_rows<MB>(cur, acc, 0.f, n, Q, 0.f, true, D, a.Tmax, pos, lane);
+      if (a.fuse_select) {
+        const int m = lane & 7, r_sel = lane >> 3, nn = n + r_sel;
+        if (r_sel < 2 && m < MB && m < Q && nn < N) {
+          float v = 0.f;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int mm = 0; mm < MB; ++mm)
+              if (r == r_sel && mm == m) v = acc[r][mm];
+          bool masked = (a.suppress_bits[nn >> 5] >> (nn & 31)) & 1u;
+          if (at_begin) masked = masked || ((a.begin_suppress_bits[nn >> 5] >> (nn & 31)) & 1u);
+          if (!masked) {
+            unsigned u = __float_as_uint(v);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)nn);
+            best = key > best ? key : best;
+          }
+        }
+      }
       buf ^= 1;
     }
+  }
+  if (a.fuse_select) {
+    // lanes m and 8 + m hold sequence m's candidates; fold per warp, per CTA, then one atomicMax per CTA and sequence
+    {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, 8);
+      best = o > best ? o : best;
+    }
+    unsigned long long* sb = reinterpret_cast<unsigned long long*>(xs);  // x is no longer needed: [MB][MW]
+    __syncthreads();
+    if (lane < MB) sb[lane * MW + warp] = best;
+    __syncthreads();
+    if (threadIdx.x < MB && threadIdx.x < Q) {
+      unsigned long long b = 0ull;
+      for (int w = 0; w < MW; ++w) b = sb[threadIdx.x * MW + w] > b ? sb[threadIdx.x * MW + w] : b;
+      if (b) atomicMax(a.sel_best + threadIdx.x, b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atom_acq_rel_add(a.sel_ctr, 1u);
+      if (prev == gridDim.x - 1) {  // every CTA's maxima are in: this is SelectArgs' greedy branch (decode.cu select_kernel)
+        const int cur_len = pos + 1;
+        const bool generating = cur_len >= a.begin_index && cur_len < a.Tmax;
+        for (int q = 0; q < Q; ++q) {
+          const unsigned long long b = __ldcg(a.sel_best + q);
+          a.sel_best[q] = 0ull;
+          if (generating) {
+            int choice = (int)(0xffffffffu - (unsigned)(b & 0xffffffffull));
+            if (a.finished[q]) choice = a.pad;
+            else if (choice == a.eos) a.finished[q] = 1;
+            a.tokens_rw[q * a.Tmax + cur_len] = choice;
+          }
+        }
+        *a.sel_ctr = 0u;
+        *a.pos_rw = pos + 1;
+      }
+    }
+  }
+  if (a.trace && bar.epoch < MEGA_TRACE_N) {  // end of this CTA's LM-head share
+    __syncthreads();
+    if (threadIdx.x == 0) a.trace[((long long)blockIdx.x * MEGA_TRACE_N + bar.epoch) * 2] = global_ns();
   }
 }
 
@@ -813,8 +891,8 @@ size_t mega_smem_plan(int mb, int D, int ffn, int num_sms, bool want_dbuf, int* 
     const int rows = (n + num_sms - 1) / num_sms, R = (rows + MW - 1) / MW;
     return (size_t)((rows + R - 1) / R * R);
   };
-  const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MAXKEYS + MW * 64) * sizeof(float);
-  const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(XKMAX + MW * 64) * sizeof(float);
+  const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MW * 72) * sizeof(float);
+  const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(MW * 72) * sizeof(float);
   const size_t att = ATT_OFF + (attn > xattn ? attn : xattn);
   const size_t lm = (size_t)MW * 2 * 2 * D * 2;  // LM head: 2 stages of row pairs per warp
   size_t r1 = rc(D) * ffn * 2;                   // region 1: out-proj / cross out-proj (K = D), fc2 (K = ffn)

@@ -70,7 +70,14 @@ i = 1 + 8 * l + 4
 base = rel[:, i - 1]
 busy = mk[:, i, 0] > 0
 out = []
-for j, lab in enumerate(("K/V + q ready", "attended", "atomic back", "merged")):
+for j, lab in enumerate(("K/V + q ready", "scores done", "max known", "PV folded")):
     d = (mk[busy, i, j] - base[busy]) / 1e3
     out.append("%s %.2f/%.2f" % (lab, np.median(d), d.max()))
 print("  E cross  " + "  ".join(out))
+
+dns = (mk[busy, i, 1] - mk[busy, i, 0]).astype(np.float64)
+dcy = (mk[busy, i, 3] - mk[busy, i, 2]).astype(np.float64)
+print("  SM clock during E (cycles / ns between two marks): median %.3f GHz (ns %.0f, cycles %.0f)" % (np.median(dcy / dns), np.median(dns), np.median(dcy)))
+
+end = tr[:, nb, 0]
+print("LM head (last barrier release -> CTA done): median %.1f us, max %.1f us" % (np.median(end - rel[:, nb - 1].max()) / 1e3, (end.max() - rel[:, nb - 1].max()) / 1e3))
