@@ -89,6 +89,9 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt_ho
                     const bw_decode_opts* opts, void* stream);
 /* run n decoder steps (one CUDA-graph launch each, no host synchronisation) */
 int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream);
+/* kernels launched by bw_decode_run since the engine was created (kernel nodes of the step graph x graph launches);
+ * bench.py reports it as part of "gpu_launches" */
+long long bw_decode_kernel_launches(bw_engine* e);
 /* synchronises the stream; tokens_host [A*G, max_target_positions], finished_host [A*G] (either may be NULL) */
 int bw_decode_read(bw_engine* e, int32_t* tokens_host, int32_t* finished_host, int32_t* pos_host, void* stream);
 /* beam search support: reorder sequences (new sequence i continues old sequence parent[i]) by permuting the

@@ -86,6 +86,8 @@ struct bw_engine {
   bool use_anc = false;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   cudaGraphExec_t cur_graph = nullptr;
+  std::map<cudaGraphExec_t, int> graph_kernels;  // kernel nodes of each captured step graph
+  long long step_kernel_launches = 0;            // kernels launched by bw_decode_run so far (graph path)
   bool no_graph = false, simt = false, no_mega = false;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
@@ -633,9 +635,23 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
         if (rc == 0) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
         return -1;
       }
+      int n_kernel_nodes = 0;
+      {
+        size_t nn = 0;
+        if (cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess && nn > 0) {
+          std::vector<cudaGraphNode_t> nodes(nn);
+          if (cudaGraphGetNodes(graph, nodes.data(), &nn) == cudaSuccess) {
+            for (size_t i = 0; i < nn; ++i) {
+              cudaGraphNodeType ty;
+              if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++n_kernel_nodes;
+            }
+          }
+        }
+      }
       cudaGraphExec_t exec = nullptr;
       BW_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
+      e->graph_kernels[exec] = n_kernel_nodes;
       cudaStreamDestroy(cs);
       it = e->graphs.emplace(key, exec).first;
     }
@@ -650,12 +666,15 @@ int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream) {
   for (int i = 0; i < n_steps; ++i) {
     if (e->cur_graph) {
       BW_CUDA_OK(cudaGraphLaunch(e->cur_graph, st));
+      e->step_kernel_launches += e->graph_kernels[e->cur_graph];
     } else {
       if (int rc = step_impl(e, st)) return rc;
     }
   }
   return 0;
 }
+
+long long bw_decode_kernel_launches(bw_engine* e) { return e ? e->step_kernel_launches : -1; }
 
 int bw_decode_read(bw_engine* e, int32_t* tokens_host, int32_t* finished_host, int32_t* pos_host, void* stream) {
   BW_CHECK(e && e->finalized && e->Q > 0, "bw_decode_read: no decode in progress");

@@ -260,6 +260,10 @@ class WhisperEngine:
     def decode_run(self, n_steps: int) -> None:
         _lib.check(self.lib.bw_decode_run(self.h, n_steps, self._stream()))
 
+    def decode_kernel_launches(self) -> int:
+        """Kernels launched by decode_run so far (counted from the captured step graphs)."""
+        return int(self.lib.bw_decode_kernel_launches(self.h))
+
     def decode_read(self):
         """-> (tokens [Q, Tmax] int32, finished [Q] int32, pos)"""
         Q = self._Q
