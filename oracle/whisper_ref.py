@@ -38,15 +38,17 @@ def logmel_np(audio: np.ndarray, bank: np.ndarray, n_samples: int) -> np.ndarray
 # ------------------------------------------------------------------------------------------------------------------
 def process_logits(scores: np.ndarray, seq: Sequence[int], begin_index: int, *, suppress: Sequence[int] = (),
                    begin_suppress: Sequence[int] = (), ts_rules: bool = False, ts_begin: int = 50365, no_ts: int = 50364,
-                   eos: int = 50257, max_initial_ts: Optional[int] = None) -> np.ndarray:
-    """One row of logits through SuppressTokensAtBegin -> SuppressTokens -> WhisperTimeStamp; seq = all tokens so far."""
+                   eos: int = 50257, max_initial_ts: Optional[int] = None, details: bool = False):
+    """One row of logits through SuppressTokensAtBegin -> SuppressTokens -> WhisperTimeStamp; seq = all tokens so far.
+    details=True returns (processed, processed-before-the-probability-rule, ts_logprob - max text logprob): the last rule
+    (TF/generation/logits_process.py:2034-2041) is a discrete comparison, so tie-aware parity checks need its margin."""
     s = np.array(scores, dtype=np.float32, copy=True)
     if len(seq) == begin_index and len(begin_suppress):
         s[list(begin_suppress)] = -np.inf
     if len(suppress):
         s[list(suppress)] = -np.inf
     if not ts_rules:
-        return s
+        return (s, s.copy(), float("nan")) if details else s
     s[no_ts] = -np.inf
     sampled = list(seq[begin_index:])
     last_ts = len(sampled) >= 1 and sampled[-1] >= ts_begin
@@ -70,9 +72,11 @@ def process_logits(scores: np.ndarray, seq: Sequence[int], begin_index: int, *, 
     ts_part = logp[ts_begin:]
     tm = ts_part.max()
     ts_lp = tm + np.log(np.exp(ts_part - tm).sum()) if np.isfinite(tm) else -np.inf
+    pre = s.copy()
+    rule_margin = float(ts_lp - logp[:ts_begin].max())
     if ts_lp > logp[:ts_begin].max():
         s[:ts_begin] = -np.inf
-    return s
+    return (s, pre, rule_margin) if details else s
 
 
 # ------------------------------------------------------------------------------------------------------------------

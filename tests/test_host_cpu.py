@@ -147,6 +147,29 @@ def test_pipeline_host_logic_matches_reference(monkeypatch, mode):
     assert _same(norm, ref), (norm, ref)
 
 
+def test_oracle_replay_checker_on_stub(monkeypatch):
+    """The tie-aware replay used by the GPU pipeline tests (tests/parity_utils.py) finds zero near ties when the engine
+    is the fp32 CPU stand-in: recorder hooks, prompt/EOS bookkeeping and the logits rules line up with the oracle."""
+    from tests.parity_utils import DecodeRecorder, assert_oracle_greedy
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, "model_tiny10.json")))
+    pipe = _stub_pipeline(monkeypatch, meta["preset"], meta["layer_gain"], meta["chunk_s"], batch_size=2)
+    rec = DecodeRecorder(pipe)
+    audio = S.synth_audio(meta["audio_s"], seed=2000)
+    gk = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": 24}
+    pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=2, return_timestamps="word", generate_kwargs=dict(gk))
+    from oracle import hf_ref
+
+    om = S.make_hf_model(meta["preset"], seed=0, layer_gain=meta["layer_gain"])
+    hf_ref.interpolate_positions(om, meta["chunk_s"])
+    assert sum(len(g) for r in rec.records for g in r["gen"]) >= 8
+    assert assert_oracle_greedy(rec.records, om) == 0
+    rec2 = DecodeRecorder(pipe)
+    pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=2, generate_kwargs=dict(gk))
+    assert assert_oracle_greedy(rec2.records, om) == 0
+
+
 def test_window_schedule_matches_transformers():
     from transformers.pipelines.automatic_speech_recognition import chunk_iter
 

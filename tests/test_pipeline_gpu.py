@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 
 from tests.conftest import GOLD
+from tests.parity_utils import DecodeRecorder as _DecodeRecorder, assert_oracle_greedy as _assert_oracle_greedy
 
 pytestmark = pytest.mark.gpu
 
@@ -101,19 +102,29 @@ def test_pipeline_beam_search_matches_reference(cuda):
 
 
 def test_pipeline_vs_live_oracle_small30(cuda):
-    """30 s windows, 3-layer model, word timestamps, against the oracle pipeline run on the CPU in the same test."""
+    """30 s windows, 3-layer model, word timestamps, against the oracle run on the CPU in the same test.
+    (1) rigorous and tie-aware: every decode call the pipeline made is replayed through the oracle by teacher forcing --
+    each token is the oracle's processed arg-max modulo oracle near ties; (2) when no near tie occurred, text and word
+    timestamps must match the oracle PIPELINE's output (a random-weight checkpoint has top-2 margins below the bf16
+    logit error at some steps, and one flipped token changes the rest of its window, so (2) alone is box-dependent)."""
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
 
     meta, model, pipe = _pipe(chunk_s=30, batch_size=2, preset="small-test", gain=8.0)
+    rec = _DecodeRecorder(pipe)
     audio = S.synth_audio(47.0, seed=4242)
     gk = dict(GK, max_new_tokens=24)
     got = pipe(audio.copy(), chunk_length_s=29, batch_size=2, return_timestamps="word", generate_kwargs=dict(gk))
     om = S.make_hf_model("small-test", seed=0, layer_gain=8.0)
+    assert len(rec.records) >= 1 and sum(len(g) for r in rec.records for g in r["gen"]) >= 8
+    near = _assert_oracle_greedy(rec.records, om)
     ref_pipe = hf_ref.make_ref_pipeline(om, S.make_feature_extractor(30), S.make_tokenizer(), chunk_length_s=30, device="cpu", batch_size=2)
     ref = ref_pipe(audio.copy(), chunk_length_s=29, batch_size=2, return_timestamps="word", generate_kwargs=dict(gk))
-    _check_text(got["text"], ref["text"], min_prefix=4)
-    _check_words(json.loads(json.dumps(got["chunks"], default=float)), json.loads(json.dumps(ref["chunks"], default=float)))
+    if near == 0:
+        _check_text(got["text"], ref["text"], min_prefix=4)
+        _check_words(json.loads(json.dumps(got["chunks"], default=float)), json.loads(json.dumps(ref["chunks"], default=float)))
+    else:
+        _check_text(got["text"], ref["text"], min_prefix=2, min_ratio=0.3)
 
 
 def test_streaming_on_engine(cuda):

@@ -92,6 +92,8 @@ struct bw_engine {
   int mega_flags = 0, mega_nrep = 1;  // experiment switches of the persistent step kernel, re-read at every bw_decode_begin
   float* mega_rep = nullptr;
   size_t mega_rep_floats = 0;
+  unsigned long long* mega_ll = nullptr;  // flag-in-data hand-over words (decode.cuh MegaArgs::ll), zeroed per decode
+  size_t mega_ll_words = 0;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
   long long* mega_trace = nullptr;
@@ -258,6 +260,10 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.off_ml = m.off_po + r32((long long)mbq * H * ns * 64);
       m.rep_stride = m.off_ml + r32((long long)mbq * H * ns * 2);
       m.rep = e->mega_rep;
+      m.ll = e->mega_ll;
+      m.ll_off_dh = r32((long long)mbq * D);
+      m.ll_stride = m.ll_off_dh + r32((long long)mbq * ffn);
+      if ((size_t)8 * m.ll_stride > e->mega_ll_words) m.flags &= ~16;
       int nrep = e->mega_nrep;
       while (nrep > 1 && (size_t)(nrep - 1) * m.rep_stride > e->mega_rep_floats) --nrep;
       m.nrep = nrep < 1 ? 1 : nrep;
@@ -532,6 +538,8 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] (sharded: 8 counters, 32 words apart)
   e->mega_rep_floats = (size_t)7 * (2 * (2 * (size_t)D + c.ffn + (size_t)H * XSPLIT * 66) + 5 * 32);
   if (dalloc(e, "mega_rep", &e->mega_rep, e->mega_rep_floats)) return -1;
+  e->mega_ll_words = (size_t)8 * (2 * ((size_t)D + c.ffn) + 2 * 32);
+  if (dalloc(e, "mega_ll", &e->mega_ll, e->mega_ll_words)) return -1;
   {
     const char* tr = getenv("BW_MEGA_TRACE");
     if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 6)) return -1;
@@ -630,6 +638,7 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   BW_CUDA_OK(cudaMemsetAsync(e->pos, 0, sizeof(int), st));
   BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
   BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
+  BW_CUDA_OK(cudaMemsetAsync(e->mega_ll, 0, sizeof(unsigned long long) * e->mega_ll_words, st));  // tags restart with pos
   iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope

@@ -79,6 +79,44 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
+// ---- flag-in-data hand-over (MegaArgs::ll): one 64-bit word = {tag << 32 | fp32 bits}; 64-bit scalars are single-copy atomic
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __noinline__ void bar_timeout(unsigned epoch, unsigned lane);
+// Polls N groups of four consecutive words (32-byte aligned) until every tag is >= `tag`; all 2N loads of a round are in
+// flight together.  Groups with a null pointer are skipped (zeros).
+template <int N>
+__device__ __forceinline__ void ll_poll4(const unsigned long long* const (&p)[N], unsigned tag, float4 (&out)[N]) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long w[N][4];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (p[i]) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][0]), "=l"(w[i][1]) : "l"(p[i]) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][2]), "=l"(w[i][3]) : "l"(p[i] + 2) : "memory");
+      } else {
+        w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0xffffffff00000000ull;
+      }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok = ok && ((unsigned)(w[i][j] >> 32) >= tag);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = make_float4(__uint_as_float((unsigned)w[i][0]), __uint_as_float((unsigned)w[i][1]), __uint_as_float((unsigned)w[i][2]),
+                             __uint_as_float((unsigned)w[i][3]));
+      return;
+    }
+    if (clock64() - t0 > (1ll << 32)) bar_timeout(tag, 1000u + threadIdx.x);
+  }
+}
+
 // cold path of the grid barrier's polling loops (kept out of line: six inlined wait sites)
 __device__ __noinline__ void bar_timeout(unsigned epoch, unsigned lane) {
   printf("[bw] decode_mega: grid barrier %u timed out (block %d, poller %u)\n", epoch, blockIdx.x, lane);
@@ -326,12 +364,26 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     constexpr int U = 4;
     for (int base = threadIdx.x * 4; base < MB * K; base += ST * 4 * U) {
       float4 v[U];
+      if (d.ll_in) {
+        const unsigned long long* pp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * ST * 4;
+          const int m = (MB > 1 && i >= K) ? 1 : 0;
+          pp[u] = (i < MB * K && m < M) ? d.ll_in + i : nullptr;
+        }
+        ll_poll4<U>(pp, d.tag_in, v);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (!pp[u]) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = base + u * ST * 4;
         const int m = (MB > 1 && i >= K) ? 1 : 0;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
+      }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -346,10 +398,20 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   const int k = threadIdx.x * 4;
   const bool have = k < K;
   float4 v[MB];
+  if (d.ll_in) {
+    const unsigned long long* pp[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) pp[m] = (have && m < M) ? d.ll_in + (long long)m * K + k : nullptr;
+    ll_poll4<MB>(pp, d.tag_in, v);
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+      if (!pp[m]) v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
+  }
   }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
@@ -517,6 +579,9 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
     d.out[(long long)m * d.ldo + nn] = v;
     if (d.out_rep) {
       for (int c = 0; c < d.rep_extra; ++c) d.out_rep[(long long)c * d.rep_stride + (long long)m * d.ldo + nn] = v;
+    }
+    if (d.ll_out) {
+      for (int c = 0; c <= d.rep_extra; ++c) ll_store(d.ll_out + (long long)c * d.ll_stride + (long long)m * d.ldo + nn, v, d.tag_out);
     }
     if (d.kc && nn >= D) {
       const long long row = ((long long)m * Tmax + pos) * D;
@@ -765,7 +830,9 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
-    bar.arrive();
+    // flag-in-data hand-over: the results of this phase carry their own tags and the next phase polls them -- no grid barrier
+    const bool handover = cur.ll_out != nullptr;
+    if (!handover) bar.arrive();
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
       long long t0 = 0, t1 = 0;
       for (int w = 0; w < MW; ++w) {
@@ -945,7 +1012,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       bar.sync();
     } else {
-      bar.wait();
+      if (!handover) bar.wait();
     }
   }
 
