@@ -89,11 +89,7 @@ struct bw_engine {
   std::map<cudaGraphExec_t, int> graph_kernels;  // kernel nodes of each captured step graph
   long long step_kernel_launches = 0;            // kernels launched by bw_decode_run so far (graph path)
   bool no_graph = false, simt = false, no_mega = false;
-  int mega_flags = 0, mega_nrep = 1;  // experiment switches of the persistent step kernel, re-read at every bw_decode_begin
-  float* mega_rep = nullptr;
-  size_t mega_rep_floats = 0;
-  unsigned long long* mega_ll = nullptr;  // flag-in-data hand-over words (decode.cuh MegaArgs::ll), zeroed per decode
-  size_t mega_ll_words = 0;
+  int mega_flags = 0;  // BW_MEGA_FLAGS, re-read at every bw_decode_begin (each value has its own step graph)
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
   long long* mega_trace = nullptr;
@@ -238,7 +234,7 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     int ns = e->num_sms / (Q * H);
     const int ns_min = (S + 255) / 256;
     if (ns < ns_min) ns = ns_min;
-    if (ns > 8) ns = 8;  // decode_mega.cu MXS
+    if (ns > XSPLIT) ns = XSPLIT;
     m.nsplit = ns;
     if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
       m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
@@ -251,23 +247,6 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.sel_best = e->sel_best; m.sel_ctr = e->sel_ctr;
     }
     m.flags = e->mega_flags;
-    {  // replicated activations (decode.cuh MegaArgs::rep): offsets of one copy, every region a multiple of 32 floats
-      auto r32 = [](long long n) { return (int)((n + 31) / 32 * 32); };
-      const int mbq = Q <= 1 ? 1 : 2;
-      m.off_dattn = r32((long long)mbq * D);
-      m.off_dh = m.off_dattn + r32((long long)mbq * D);
-      m.off_po = m.off_dh + r32((long long)mbq * ffn);
-      m.off_ml = m.off_po + r32((long long)mbq * H * ns * 64);
-      m.rep_stride = m.off_ml + r32((long long)mbq * H * ns * 2);
-      m.rep = e->mega_rep;
-      m.ll = e->mega_ll;
-      m.ll_off_dh = r32((long long)mbq * D);
-      m.ll_stride = m.ll_off_dh + r32((long long)mbq * ffn);
-      if ((size_t)8 * m.ll_stride > e->mega_ll_words) m.flags &= ~16;
-      int nrep = e->mega_nrep;
-      while (nrep > 1 && (size_t)(nrep - 1) * m.rep_stride > e->mega_rep_floats) --nrep;
-      m.nrep = nrep < 1 ? 1 : nrep;
-    }
     const int rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;
@@ -535,11 +514,7 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
-  if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] (sharded: 8 counters, 32 words apart)
-  e->mega_rep_floats = (size_t)7 * (2 * (2 * (size_t)D + c.ffn + (size_t)H * XSPLIT * 66) + 5 * 32);
-  if (dalloc(e, "mega_rep", &e->mega_rep, e->mega_rep_floats)) return -1;
-  e->mega_ll_words = (size_t)8 * (2 * ((size_t)D + c.ffn) + 2 * 32);
-  if (dalloc(e, "mega_ll", &e->mega_ll, e->mega_ll_words)) return -1;
+  if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] + per-CTA flags [32, 32 + SMs)
   {
     const char* tr = getenv("BW_MEGA_TRACE");
     if (tr && tr[0] == '1' && dalloc(e, "mega_trace", &e->mega_trace, (size_t)e->num_sms * MEGA_TRACE_N * 6)) return -1;
@@ -638,24 +613,19 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   BW_CUDA_OK(cudaMemsetAsync(e->pos, 0, sizeof(int), st));
   BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
   BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
-  BW_CUDA_OK(cudaMemsetAsync(e->mega_ll, 0, sizeof(unsigned long long) * e->mega_ll_words, st));  // tags restart with pos
   iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
   e->cur_graph = nullptr;
-  {  // experiment switches are re-read per decode so one process can A/B them (each combination has its own graph)
+  {  // experiment switches are re-read per decode so one process can A/B them (tools/mega_ab.py)
     const char* fl = getenv("BW_MEGA_FLAGS");
-    e->mega_flags = fl ? atoi(fl) : MEGA_DEFAULT_FLAGS;
-    const char* nr = getenv("BW_MEGA_REP");
-    e->mega_nrep = nr ? atoi(nr) : MEGA_DEFAULT_REP;
-    if (e->mega_nrep < 1) e->mega_nrep = 1;
-    if (e->mega_nrep > 8) e->mega_nrep = 8;
+    e->mega_flags = fl ? atoi(fl) : 0;
     const char* nm = getenv("BW_NO_MEGA");
     e->no_mega = nm && nm[0] == '1';
   }
   if (!e->no_graph) {
     GraphKey key{A, G, opts->begin_index, opts->timestamp_rules * 4 + (opts->max_initial_timestamp_index + 1) * 8, opts->record_alignment,
-                 e->mega_flags * 16 + e->mega_nrep + (e->no_mega ? 4096 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 8192 : 0)};
+                 e->mega_flags * 4 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0)};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
       cudaStream_t cs;

@@ -86,8 +86,6 @@ struct MegaLayer {
 };
 
 constexpr int MEGA_MAXL = 32;
-constexpr int MEGA_DEFAULT_FLAGS = 0;  // MegaArgs::flags when BW_MEGA_FLAGS is unset
-constexpr int MEGA_DEFAULT_REP = 1;    // MegaArgs::nrep when BW_MEGA_REP is unset
 constexpr int MEGA_TRACE_N = 264;  // barriers per step that the optional trace records
 
 struct MegaArgs {
@@ -109,22 +107,7 @@ struct MegaArgs {
   float* align;
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
-  int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments);
-                     // bit2: grid barrier sharded over 8 counters; bit3: the consumer phase merges the cross-attention
-                     // partials (no last-arriver merge); bit4: flag-in-data hand-over between GEMV phases (see ll)
-  // Replicated activations: every vector that all 148 CTAs read right after a barrier (dx, dattn, dh, the cross-attention
-  // partials) is a hot spot -- 148 requests per 128-byte line queue at ONE L2 slice (~0.3 us).  Writers store nrep
-  // copies, CTA b reads copy b % nrep.  Copy 0 is the original buffer, copy c > 0 lives at rep + (c-1)*rep_stride + offset.
-  float* rep;
-  int nrep, rep_stride, off_dattn, off_dh, off_po, off_ml;
-  // Flag-in-data hand-over (flags bit 4) for the GEMV -> GEMV transitions (out-proj -> LN2+cross-q, cross out-proj ->
-  // LN3+fc1, fc1 -> fc2, fc2 -> next layer's LN1+QKV / LM head): the producer stores each fp32 result as ONE 64-bit word
-  // {tag << 32 | bits}, the consumer's staging threads poll the words they need until the tag is current.  No release fence
-  // (store-ack round trip), no counter atomics, no separate x read after the barrier: the four grid barriers of those
-  // transitions disappear.  tag = ((pos + 1) << 8) + producer phase + 1, strictly increasing within a decode; the buffers are
-  // zeroed by bw_decode_begin.  Copy c of dx lives at ll + c*ll_stride, dh at + ll_off_dh (nrep copies, as for rep).
-  unsigned long long* ll;
-  int ll_stride, ll_off_dh;
+  int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments)
   // greedy token selection fused behind the LM head (no timestamp rules, one beam): masked arg-max by 64-bit atomicMax,
   // the last CTA to finish writes the token, handles EOS / pad and advances the position -- no select kernel
   int fuse_select;

@@ -39,7 +39,6 @@ constexpr int DMA_T = MT - 32;  // first lane of the last warp: issues every TMA
 constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
 constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
 constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
-constexpr int MXS = 8;         // max key splits per (sequence, head) here (the per-op kernels allow XSPLIT): bounds the unrolled merges
 constexpr int MAXD = 1280;
 constexpr int ATT_OFF = 32 * 1024;  // attention scratch starts here inside the pool (above the R=1 weight slabs)
 
@@ -79,50 +78,6 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
-// ---- flag-in-data hand-over (MegaArgs::ll): one 64-bit word = {tag << 32 | fp32 bits}; 64-bit scalars are single-copy atomic
-__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned tag) {
-  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __noinline__ void bar_timeout(unsigned epoch, unsigned lane);
-// Polls N groups of four consecutive words (32-byte aligned) until every tag is >= `tag`; all 2N loads of a round are in
-// flight together.  Groups with a null pointer are skipped (zeros).
-template <int N>
-__device__ __forceinline__ void ll_poll4(const unsigned long long* const (&p)[N], unsigned tag, float4 (&out)[N]) {
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned long long w[N][4];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (p[i]) {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][0]), "=l"(w[i][1]) : "l"(p[i]) : "memory");
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][2]), "=l"(w[i][3]) : "l"(p[i] + 2) : "memory");
-      } else {
-        w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0xffffffff00000000ull;
-      }
-    }
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ok = ok && ((unsigned)(w[i][j] >> 32) >= tag);
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        out[i] = make_float4(__uint_as_float((unsigned)w[i][0]), __uint_as_float((unsigned)w[i][1]), __uint_as_float((unsigned)w[i][2]),
-                             __uint_as_float((unsigned)w[i][3]));
-      return;
-    }
-    if (clock64() - t0 > (1ll << 32)) bar_timeout(tag, 1000u + threadIdx.x);
-  }
-}
-
-// cold path of the grid barrier's polling loops (kept out of line: six inlined wait sites)
-__device__ __noinline__ void bar_timeout(unsigned epoch, unsigned lane) {
-  printf("[bw] decode_mega: grid barrier %u timed out (block %d, poller %u)\n", epoch, blockIdx.x, lane);
-  __trap();
-}
-
 // grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel).  bar.sync orders
 // the CTA's writes before thread 0's release; the acquire poll + bar.sync orders the other CTAs' writes before our reads.
 struct GridBar {
@@ -130,8 +85,6 @@ struct GridBar {
   unsigned nblocks;
   unsigned epoch;
   long long* trace;  // optional [nblocks][2*MEGA_TRACE_N]: arrival / release time of every barrier (BW_MEGA_TRACE=1)
-  int sharded;       // 1: CTA b arrives on counter (b & 7) (128 bytes apart: 8 L2 slices share the 148 atomics), lanes 24..31
-                     // of the last warp poll one counter each
   // Two lessons from the timelines: (1) as a real (noinline) call the compiler waited for every in-flight prefetch load that
   // is live across it (~1 us per phase); (2) the release fence of the arriving thread waits for that thread's OWN outstanding
   // loads -- so the arriving thread is the CTA's last one, which never has a prefetch load in flight (it owns no LayerNorm
@@ -141,34 +94,20 @@ struct GridBar {
   __device__ __forceinline__ void arrive() {
     if (threadIdx.x == MT - 1) {
       if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
-      red_release_add(sharded ? ctr + (blockIdx.x & 7u) * 32u : ctr, 1u);
+      red_release_add(ctr, 1u);
     }
   }
   // (a per-CTA flag array polled by one warp instead of the single counter was tried: 3+ us per barrier)
   __device__ __forceinline__ void wait() {
-    if (sharded) {
-      if (threadIdx.x >= MT - 8) {
-        const unsigned i = threadIdx.x - (MT - 8);
-        const unsigned cnt = (nblocks > i) ? (nblocks - i + 7u) >> 3 : 0u;  // CTAs b < nblocks with (b & 7) == i
-        const unsigned target = (epoch + 1) * cnt;
-        const long long t0 = clock64();
-        for (;;) {
-          const bool ok = ld_acquire_u32(ctr + i * 32u) >= target;
-          if (__all_sync(0xff000000u, ok)) break;
-          if (clock64() - t0 > (1ll << 32)) bar_timeout(epoch, i);
-        }
-        if (threadIdx.x == MT - 1 && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
-      }
-      ++epoch;
-      __syncthreads();
-      return;
-    }
     if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
       if (ld_acquire_u32(ctr) < target) {
         const long long t0 = clock64();
         while (ld_acquire_u32(ctr) < target) {
-          if (clock64() - t0 > (1ll << 32)) bar_timeout(epoch, 0u);
+          if (clock64() - t0 > (1ll << 32)) {
+            printf("[bw] decode_mega: grid barrier %u timed out (block %d)\n", epoch, blockIdx.x);
+            __trap();
+          }
         }
       }
       if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
@@ -199,13 +138,6 @@ struct GemvDesc {
   float alpha;            // rows < alpha_cols are scaled (q * 1/sqrt(dh))
   int alpha_cols;
   bf16 *kc, *vc;          // optional self-KV append (fused QKV): rows [D, 2D) -> kc, [2D, 3D) -> vc at position pos
-  float* out_rep;         // copies 1.. of `out` (same row pitch), rep_stride floats apart; nullptr: not replicated
-  int rep_extra, rep_stride;
-  // flag-in-data hand-over (MegaArgs::ll): where this phase polls its x / publishes its results (nullptr: plain + barrier)
-  const unsigned long long* ll_in;
-  unsigned long long* ll_out;  // copy 0; the other nrep - 1 copies are ll_stride words apart
-  int ll_stride;
-  unsigned tag_in, tag_out;
 };
 
 // g: 0 LN1+QKV | 1 self out-proj | 2 LN2+cross q | 3 cross out-proj | 4 LN3+fc1+GELU | 5 fc2; l == a.L: final LN + LM head
@@ -215,39 +147,8 @@ __device__ __forceinline__ void split_rows(GemvDesc& d) {
   d.n0 = min(d.N, (int)blockIdx.x * rc);
   d.nend = min(d.N, d.n0 + rc);
 }
-// copy `c` of a replicated activation vector (MegaArgs::rep): copy 0 is the original buffer
-__device__ __forceinline__ float* rep_copy(const MegaArgs& a, float* base, int off, int c) {
-  return c == 0 ? base : a.rep + (long long)(c - 1) * a.rep_stride + off;
-}
-__device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g, int pos) {
+__device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g) {
   GemvDesc d;
-  {
-    const bool ll = (a.flags & 16) != 0;
-    const int ph = l * 6 + g;  // (the LM head is phase 6 * L)
-    const unsigned base = ((unsigned)pos + 1u) << 8;
-    const int c = (a.nrep > 1) ? (int)(blockIdx.x % (unsigned)a.nrep) : 0;
-    const unsigned long long* mine = a.ll + (long long)c * a.ll_stride;
-    d.ll_in = nullptr;
-    d.ll_out = nullptr;
-    d.ll_stride = a.ll_stride;
-    d.tag_in = base + (unsigned)ph;        // = tag_out of phase ph - 1
-    d.tag_out = base + (unsigned)ph + 1u;
-    if (ll) {
-      if (g == 2 || g == 4 || (g == 0 && l > 0)) d.ll_in = mine;  // dx published by out-proj / cross out-proj / fc2
-      if (g == 5) d.ll_in = mine + a.ll_off_dh;                    // dh published by fc1
-      if (l < a.L) {
-        if (g == 1 || g == 3 || g == 5) d.ll_out = a.ll;
-        if (g == 4) d.ll_out = a.ll + a.ll_off_dh;
-      }
-    }
-  }
-  const int myc = (a.nrep > 1) ? (int)(blockIdx.x % (unsigned)a.nrep) : 0;
-  const float* const dx_in = rep_copy(a, a.dx, 0, myc);
-  const float* const dattn_in = rep_copy(a, a.dattn, a.off_dattn, myc);
-  d.out_rep = nullptr;
-  d.rep_extra = a.nrep - 1;
-  d.rep_stride = a.rep_stride;
-  float* const dx_rep = (a.nrep > 1) ? a.rep : nullptr;
   d.lng = d.lnb = nullptr;
   d.residual = nullptr;
   d.act = 0;
@@ -257,30 +158,29 @@ __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer
   d.N = d.K = d.ldo = a.D;
   d.lm = false;
   if (l >= a.L) {
-    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.n0 = 0; d.nend = a.V; d.lm = true; d.src = dx_in; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.V;
+    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.n0 = 0; d.nend = a.V; d.lm = true; d.src = a.dx; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.V;
     return d;
   }
   const MegaLayer& L = layers[l];
   switch (g) {
     case 0:
-      d.W = L.wqkv; d.bias = L.bqkv; d.N = 3 * a.D; d.src = dx_in; d.lng = L.ln1g; d.lnb = L.ln1b; d.out = a.dqkv; d.ldo = 3 * a.D;
+      d.W = L.wqkv; d.bias = L.bqkv; d.N = 3 * a.D; d.src = a.dx; d.lng = L.ln1g; d.lnb = L.ln1b; d.out = a.dqkv; d.ldo = 3 * a.D;
       d.alpha = 0.125f; d.alpha_cols = a.D; d.kc = L.self_k; d.vc = L.self_v;
       break;
     case 1:
-      d.W = L.wo; d.bias = L.bo; d.src = dattn_in; d.out = a.dx; d.residual = a.dx; d.out_rep = dx_rep;
+      d.W = L.wo; d.bias = L.bo; d.src = a.dattn; d.out = a.dx; d.residual = a.dx;
       break;
     case 2:
-      d.W = L.xwq; d.bias = L.xbq; d.src = dx_in; d.lng = L.ln2g; d.lnb = L.ln2b; d.out = a.dq; d.alpha = 0.125f; d.alpha_cols = a.D;
+      d.W = L.xwq; d.bias = L.xbq; d.src = a.dx; d.lng = L.ln2g; d.lnb = L.ln2b; d.out = a.dq; d.alpha = 0.125f; d.alpha_cols = a.D;
       break;
     case 3:
-      d.W = L.xwo; d.bias = L.xbo; d.src = dattn_in; d.out = a.dx; d.residual = a.dx; d.out_rep = dx_rep;
+      d.W = L.xwo; d.bias = L.xbo; d.src = a.dattn; d.out = a.dx; d.residual = a.dx;
       break;
     case 4:
-      d.W = L.w1; d.bias = L.b1; d.N = a.ffn; d.src = dx_in; d.lng = L.ln3g; d.lnb = L.ln3b; d.out = a.dh; d.ldo = a.ffn; d.act = 1;
-      d.out_rep = (a.nrep > 1) ? a.rep + a.off_dh : nullptr;
+      d.W = L.w1; d.bias = L.b1; d.N = a.ffn; d.src = a.dx; d.lng = L.ln3g; d.lnb = L.ln3b; d.out = a.dh; d.ldo = a.ffn; d.act = 1;
       break;
     default:
-      d.W = L.w2; d.bias = L.b2; d.K = a.ffn; d.src = rep_copy(a, a.dh, a.off_dh, myc); d.out = a.dx; d.residual = a.dx; d.out_rep = dx_rep;
+      d.W = L.w2; d.bias = L.b2; d.K = a.ffn; d.src = a.dh; d.out = a.dx; d.residual = a.dx;
       break;
   }
   split_rows(d);
@@ -364,26 +264,12 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     constexpr int U = 4;
     for (int base = threadIdx.x * 4; base < MB * K; base += ST * 4 * U) {
       float4 v[U];
-      if (d.ll_in) {
-        const unsigned long long* pp[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * ST * 4;
-          const int m = (MB > 1 && i >= K) ? 1 : 0;
-          pp[u] = (i < MB * K && m < M) ? d.ll_in + i : nullptr;
-        }
-        ll_poll4<U>(pp, d.tag_in, v);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (!pp[u]) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = base + u * ST * 4;
         const int m = (MB > 1 && i >= K) ? 1 : 0;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
-      }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -398,20 +284,10 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   const int k = threadIdx.x * 4;
   const bool have = k < K;
   float4 v[MB];
-  if (d.ll_in) {
-    const unsigned long long* pp[MB];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) pp[m] = (have && m < M) ? d.ll_in + (long long)m * K + k : nullptr;
-    ll_poll4<MB>(pp, d.tag_in, v);
-#pragma unroll
-    for (int m = 0; m < MB; ++m)
-      if (!pp[m]) v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-  } else {
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
     v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
-  }
   }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
@@ -448,65 +324,6 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
       o.z = (v[m].z - mean[m]) * rstd * p.g.z + p.b.z;
       o.w = (v[m].w - mean[m]) * rstd * p.g.w + p.b.w;
       *reinterpret_cast<float4*>(xs + m * K + k) = o;
-    }
-  }
-  __syncthreads();
-}
-
-// Phase F staging when the consumer merges the cross-attention partials (MegaArgs::flags bit 3): x[m][h*64 + d] =
-// sum_s w_s o_s[d] / sum_s w_s l_s with w_s = exp(m_s - max m) -- the same arithmetic, in the same order, as the
-// last-arriver merge in phase E.  Each CTA reads the Q*H*nsplit partial rows (36 KB at 20 heads x 7 splits) instead of the
-// 5 KB merged vector, but phase E loses an atomic round trip and a dependent second pass (~1.9 us on its critical path).
-template <int MB, class Dma>
-__device__ __forceinline__ void stage_merge(float* xs, const MegaArgs& a, const float* po, const float* pml, int M, Dma&& dma) {
-  if ((threadIdx.x >> 5) == MW - 1) {
-    dma();
-    __syncthreads();
-    return;
-  }
-  const int k = threadIdx.x * 4;
-  const int D = a.D, H = a.H, ns = a.nsplit;
-  if (k < D) {
-    const int h = k >> 6, dd = k & 63;
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M) {
-        const long long hb = ((long long)m * H + h) * ns;
-        // every load is issued before anything is consumed: one L2 round trip, not a dependent chain
-        float w[MXS], pl[MXS];
-        float4 o[MXS];
-#pragma unroll
-        for (int sp = 0; sp < MXS; ++sp) {
-          w[sp] = -INFINITY;
-          pl[sp] = 0.f;
-          o[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (sp < ns) {
-            const float2 ml = __ldcg(reinterpret_cast<const float2*>(pml + (hb + sp) * 2));
-            w[sp] = ml.x;
-            pl[sp] = ml.y;
-            o[sp] = __ldcg(reinterpret_cast<const float4*>(po + (hb + sp) * 64 + dd));
-          }
-        }
-        float Mx = -INFINITY;
-#pragma unroll
-        for (int sp = 0; sp < MXS; ++sp)
-          if (pl[sp] > 0.f) Mx = fmaxf(Mx, w[sp]);
-        float Ls = 0.f;
-#pragma unroll
-        for (int sp = 0; sp < MXS; ++sp) {
-          if (pl[sp] > 0.f) {
-            const float e = __expf(w[sp] - Mx);
-            Ls = fmaf(pl[sp], e, Ls);
-            r.x = fmaf(o[sp].x, e, r.x);
-            r.y = fmaf(o[sp].y, e, r.y);
-            r.z = fmaf(o[sp].z, e, r.z);
-            r.w = fmaf(o[sp].w, e, r.w);
-          }
-        }
-        r.x /= Ls; r.y /= Ls; r.z /= Ls; r.w /= Ls;
-      }
-      *reinterpret_cast<float4*>(xs + m * D + k) = r;
     }
   }
   __syncthreads();
@@ -577,12 +394,6 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
     if (d.act == 1) v = gelu_erf(v);
     if (d.residual) v += res_valid ? res : __ldcg(d.residual + (long long)m * d.ldo + nn);
     d.out[(long long)m * d.ldo + nn] = v;
-    if (d.out_rep) {
-      for (int c = 0; c < d.rep_extra; ++c) d.out_rep[(long long)c * d.rep_stride + (long long)m * d.ldo + nn] = v;
-    }
-    if (d.ll_out) {
-      for (int c = 0; c <= d.rep_extra; ++c) ll_store(d.ll_out + (long long)c * d.ll_stride + (long long)m * d.ldo + nn, v, d.tag_out);
-    }
     if (d.kc && nn >= D) {
       const long long row = ((long long)m * Tmax + pos) * D;
       if (nn < 2 * D) d.kc[row + nn - D] = __float2bfloat16(v);
@@ -718,10 +529,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int gw = blockIdx.x * MW + warp, GW = gridDim.x * MW;
   const int D = a.D, H = a.H, Q = a.Q;
   const int pos = *a.pos;
-  GridBar bar{a.bar, gridDim.x, 0u, a.trace, (a.flags & 4) ? 1 : 0};
-  const int nrep = a.nrep;
-  const int myc = (nrep > 1) ? (int)(blockIdx.x % (unsigned)nrep) : 0;
-  const bool cmerge = (a.flags & 8) != 0;  // phase F merges the cross-attention partials while staging its x
+  GridBar bar{a.bar, gridDim.x, 0u, a.trace};
   long long* const mkbase = a.trace ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + (long long)blockIdx.x * MEGA_TRACE_N * 4 : nullptr;
   auto mark = [&](int j) {
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) mkbase[bar.epoch * 4 + j] = global_ns();
@@ -748,7 +556,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   __syncthreads();
 
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
-  GemvDesc cur = make_desc(a, sl, 0, 0, pos);
+  GemvDesc cur = make_desc(a, sl, 0, 0);
   Pre pre;
   // Slab regions: GEMV phase ph (= 6*layer + g) lives in region ph & 1 -- region 1 at the pool's start (out-proj, cross
   // out-proj, fc2), region 0 at p0_off (QKV, cross-q, fc1).  Double-buffered (p0_off > 0), the copy for phase ph + 1 is
@@ -762,9 +570,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
       const int tok = a.tokens[q * a.Tmax + pos];
-      const float v = __bfloat162float(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
-      a.dx[i] = v;
-      for (int c = 1; c < nrep; ++c) rep_copy(a, a.dx, 0, c)[i] = v;
+      a.dx[i] = __bfloat162float(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
     }
   }
   bar.sync();
@@ -788,12 +594,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         // layer is ~54 MB = 8 us of HBM time spread over ~35 us, but a 13 MB slab set requested only one barrier before its
         // use is still arriving when the phase starts, and the barrier's own atomics queue behind it
         if (dbuf && ph + 1 < nph) {
-          const GemvDesc d1 = make_desc(a, sl, (ph + 1) / 6, (ph + 1) % 6, pos);
+          const GemvDesc d1 = make_desc(a, sl, (ph + 1) / 6, (ph + 1) % 6);
           issue_slabs(d1, pool + (((ph + 1) & 1) ? 0 : a.p0_off), &cbar[(ph + 1) & 1]);
         }
         if (!(a.flags & 1)) {
           if (ph + 2 <= nph) {
-            const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6, pos);
+            const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
             l2_prefetch_phase(d2);
           }
           if (g == 0 && threadIdx.x == DMA_T + 1 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
@@ -808,8 +614,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
         }
       };
-      if (cmerge && g == 3) stage_merge<MB>(xs, a, rep_copy(a, a.part_o, a.off_po, myc), rep_copy(a, a.part_ml, a.off_ml, myc), Q, ahead);
-      else stage_x<MB>(xs, red, cur, pre, Q, ahead);
+      stage_x<MB>(xs, red, cur, pre, Q, ahead);
       mark(2);
       if (mkbase && lane == 0) wts[warp][0] = wts[warp][1] = 0;
       if (active) {
@@ -830,9 +635,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
-    // flag-in-data hand-over: the results of this phase carry their own tags and the next phase polls them -- no grid barrier
-    const bool handover = cur.ll_out != nullptr;
-    if (!handover) bar.arrive();
+    bar.arrive();
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
       long long t0 = 0, t1 = 0;
       for (int w = 0; w < MW; ++w) {
@@ -842,7 +645,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       mkbase[bar.epoch * 4 + 0] = t0;
       mkbase[bar.epoch * 4 + 1] = t1;
     }
-    cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6, pos);
+    cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6);
     if (!dbuf && !cur.lm) issue_slabs(cur, pool, &cbar[(ph + 1) & 1]);
     prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
 
@@ -883,12 +686,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         float mx, sum, ov;
         if (n <= 3 * KG) attend_smem<3>(sK, sV, redo, red, qv, n, nullptr, mx, sum, ov);
         else attend_smem<(MAXKEYS + KG - 1) / KG>(sK, sV, redo, red, qv, n, nullptr, mx, sum, ov);
-        if (threadIdx.x < 64) {
-          const float o = ov / sum;
-          const long long di = (long long)q * D + h * 64 + threadIdx.x;
-          a.dattn[di] = o;
-          for (int c = 1; c < nrep; ++c) rep_copy(a, a.dattn, a.off_dattn, c)[di] = o;
-        }
+        if (threadIdx.x < 64) a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / sum;
         fence_proxy_async_smem();  // this thread's scratch writes (generic proxy) before later TMA writes to the same bytes
         __syncthreads();
       }
@@ -951,20 +749,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
             a.part_ml[pb * 2 + 0] = mx;
             a.part_ml[pb * 2 + 1] = sum;
           }
-          if (cmerge) {  // the consumer (cross out-proj staging, every CTA) merges: no counter round trip, no second pass here
-            if (threadIdx.x < 64) {
-              for (int c = 1; c < nrep; ++c) rep_copy(a, a.part_o, a.off_po, c)[pb * 64 + threadIdx.x] = ov;
-            } else if (threadIdx.x == 64) {
-              for (int c = 1; c < nrep; ++c) {
-                float* ml = rep_copy(a, a.part_ml, a.off_ml, c);
-                ml[pb * 2 + 0] = mx;
-                ml[pb * 2 + 1] = sum;
-              }
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            continue;
-          }
           // merge by the last-arriving split of this (sequence, head): the partial stores above happen-before thread 0's
           // acq_rel atomic through the CTA barrier; the last arriver's acquire makes every split's partials visible
           __syncthreads();
@@ -975,9 +759,9 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           __syncthreads();
           if (s_last && threadIdx.x < 64) {
             const long long hb = ((long long)q * H + h) * nsplit;
-            float pm[MXS], pl[MXS], po[MXS];
+            float pm[XSPLIT], pl[XSPLIT], po[XSPLIT];
 #pragma unroll
-            for (int sp = 0; sp < MXS; ++sp) {
+            for (int sp = 0; sp < XSPLIT; ++sp) {
               pm[sp] = -INFINITY; pl[sp] = 0.f; po[sp] = 0.f;
               if (sp < nsplit) {
                 pm[sp] = __ldcg(&a.part_ml[(hb + sp) * 2]);
@@ -987,23 +771,18 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
             }
             float M = -INFINITY;
 #pragma unroll
-            for (int sp = 0; sp < MXS; ++sp)
+            for (int sp = 0; sp < XSPLIT; ++sp)
               if (pl[sp] > 0.f) M = fmaxf(M, pm[sp]);
             float Lsum = 0.f, o = 0.f;
 #pragma unroll
-            for (int sp = 0; sp < MXS; ++sp) {
+            for (int sp = 0; sp < XSPLIT; ++sp) {
               if (pl[sp] > 0.f) {
                 const float w = __expf(pm[sp] - M);
                 Lsum = fmaf(pl[sp], w, Lsum);
                 o = fmaf(po[sp], w, o);
               }
             }
-            {
-              const float r = o / Lsum;
-              const long long di = (long long)q * D + h * 64 + threadIdx.x;
-              a.dattn[di] = r;
-              for (int c = 1; c < nrep; ++c) rep_copy(a, a.dattn, a.off_dattn, c)[di] = r;
-            }
+            a.dattn[(long long)q * D + h * 64 + threadIdx.x] = o / Lsum;
             if (threadIdx.x == 0) a.xcounters[q * H + h] = 0u;
           }
           fence_proxy_async_smem();
@@ -1012,7 +791,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       bar.sync();
     } else {
-      if (!handover) bar.wait();
+      bar.wait();
     }
   }
 
@@ -1148,7 +927,7 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
     if (((nmax + num_sms - 1) / num_sms + MW - 1) / MW > 3) return -3;
   }
   (void)GW;
-  if (a.nsplit > MXS) return -3;
+  if (a.nsplit > XSPLIT) return -3;
   const int mb = Q <= 1 ? 1 : 2;
   MegaArgs b = a;
   const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
