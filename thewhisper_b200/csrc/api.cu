@@ -247,7 +247,9 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.sel_best = e->sel_best; m.sel_ctr = e->sel_ctr;
     }
     m.flags = e->mega_flags;
-    const int rc = launch_decode_mega(st, m, e->num_sms);
+    int rc = -3;
+    if (m.flags & 32) rc = launch_decode_mega2(st, m, e->num_sms);
+    if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;
       select_done = m.fuse_select != 0;
@@ -619,7 +621,7 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   e->cur_graph = nullptr;
   {  // experiment switches are re-read per decode so one process can A/B them (tools/mega_ab.py)
     const char* fl = getenv("BW_MEGA_FLAGS");
-    e->mega_flags = fl ? atoi(fl) : 0;
+    e->mega_flags = fl ? atoi(fl) : MEGA_DEFAULT_FLAGS;
     const char* nm = getenv("BW_NO_MEGA");
     e->no_mega = nm && nm[0] == '1';
   }

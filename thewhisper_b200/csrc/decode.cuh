@@ -86,6 +86,7 @@ struct MegaLayer {
 };
 
 constexpr int MEGA_MAXL = 32;
+constexpr int MEGA_DEFAULT_FLAGS = 64;  // MegaArgs::flags when BW_MEGA_FLAGS is unset (bit 6 measured -1.2 %, bit-exact: r1_v8)
 constexpr int MEGA_TRACE_N = 264;  // barriers per step that the optional trace records
 
 struct MegaArgs {
@@ -107,7 +108,8 @@ struct MegaArgs {
   float* align;
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
-  int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments)
+  int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments);
+                     // bit5 (32): decode_mega2.cu (K-parallel GEMV phases); bit6 (64): the staging warps do not wait for the DMA warp
   // greedy token selection fused behind the LM head (no timestamp rules, one beam): masked arg-max by 64-bit atomicMax,
   // the last CTA to finish writes the token, handles EOS / pad and advances the position -- no select kernel
   int fuse_select;
@@ -124,6 +126,9 @@ struct MegaArgs {
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
+// second generation (decode_mega2.cu): K-parallel GEMV phases with x in registers, one sequence; MegaArgs::flags bit 5
+// (BW_MEGA_FLAGS=32) selects it; -3 -> the caller falls back to launch_decode_mega
+int launch_decode_mega2(cudaStream_t st, const MegaArgs& a, int num_sms);
 
 int launch_gemv(cudaStream_t st, const GemvArgs& a);
 int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax);

@@ -1,29 +1,18 @@
-// One persistent kernel per decoder step (q_len = 1, one beam per audio, up to 2 sequences).
+// Second generation of the persistent decoder-step kernel (one sequence): same phase structure, grid barrier, TMA slab
+// pipeline and attention phases as decode_mega.cu, but the six GEMV phases of a layer are K-PARALLEL with x held in
+// REGISTERS.
 //
-// Why: with one kernel per op the step is 259 launches and every op pays its own chain of dependent global round
-// trips; a step that should take 0.32 ms (2.07 GB at the measured 6.5 TB/s) took 1.7 ms
-// (profiles/r1_v1_launches_summary.md).  Here the whole step -- embedding, 32 x (LN1+QKV, self-attention, out-proj,
-// LN2+cross-q, cross-attention, out-proj, LN3+fc1+GELU, fc2), final LN + tied LM head -- runs in ONE kernel of one CTA
-// per SM, phases separated by a grid barrier.
-//
-// What the barrier timelines and ncu captures of the earlier versions taught (profiles/r1_mega_timeline.md):
-//   * a phase is only as fast as its chain of *dependent* L2/DRAM round trips (~0.6-1 us each), not its bytes: everything
-//     that does not depend on the previous phase is requested BEFORE the barrier that precedes a phase -- the weight rows
-//     of the phase (TMA bulk copies into a per-warp smem slab, one instruction per row: issuing the same bytes as 16-byte
-//     cp.async pieces cost ~1 us of LSU issue time per phase), bias values, LayerNorm gamma/beta, the attention K/V rows
-//     that are already final;
-//   * the barrier is one red.release + ld.acquire polling loop (no membar.sc / L1 invalidation; activations that cross
-//     CTAs are read with ld.global.cg);
-//   * the GEMV inner loop is bound by the 128 B/clk shared-memory port: x is LayerNormed once per CTA (not on the fly in
-//     every warp), and lanes read contiguous 16-byte (x) / 8-byte (w) pieces so no LDS has bank conflicts;
-//   * 31% of the non-barrier stall samples were instruction-cache misses: the fully inlined version was 15k SASS
-//     instructions (245 KB) walked once per layer against a 32 KB L1.5 I-cache.  The six GEMV phases of a layer are
-//     therefore ONE loop body driven by a small descriptor (make_desc), not six inlined copies.
-// After a barrier only the x row (and the residual values of the rows a warp owns) have to be fetched.
-//
-// Work split: 12 warps per CTA, global warp id gw; a GEMV phase gives warp gw the R rows starting at gw*R (one pass:
-// the launcher checks 12 * SMs * R >= N); attention phases hand (sequence, head[, key split]) items to CTAs round-robin.
-// Token selection stays a separate small kernel.
+// Why (profiles/r1_v6_summary.md, r1_v7_experiments.md): removing half of the grid barriers did not shorten the step --
+// it is bound by the critical path INSIDE a CTA between a barrier release and the CTA's own arrival: x staged to smem
+// (0.8-1.1 us), row-per-warp dot products that re-read x from smem for every row (the 128 B/clk smem port moves 3x the
+// weight bytes; fc2: 276 KB per phase, 1.7 us), epilogue.  Here thread t of the 10 compute warps owns x[c*1280 + 4t .. +3]
+// (LayerNormed in registers, statistics through two named barriers), multiplies it against the matching 8 bytes of EVERY
+// weight row of the CTA's slab (smem traffic = the weight bytes, each read once, conflict-free), the per-row partial sums
+// are folded by a transposing warp butterfly (31 shuffles for 32 rows instead of 160) and by one pass over a
+// [10 warps][rows] smem table; thread r finishes row r (bias, scale, GELU, residual, KV append).  No smem copy of x, no
+// CTA barrier between the barrier release and the dot products.  The trace instrumentation is not compiled in (code
+// size is on the critical path: 2.7 k dormant instructions cost 6 %).
+// The LM head keeps the row-pair-per-warp streaming form of decode_mega.cu (x in smem).
 #include <math.h>
 
 #include "decode.cuh"
@@ -40,6 +29,10 @@ constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
 constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
 constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
 constexpr int MAXD = 1280;
+constexpr int CW = 10;          // compute warps that hold x in registers
+constexpr int XT = CW * 32;     // their threads
+constexpr int XCH = XT * 4;     // x elements per chunk: thread t owns [c*XCH + 4t, +4), c < 4
+constexpr int MAXRC = 36;       // weight rows of one CTA in one phase (ceil(5120 / 148) = 35)
 constexpr int ATT_OFF = 32 * 1024;  // attention scratch starts here inside the pool (above the R=1 weight slabs)
 
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
@@ -85,19 +78,14 @@ struct GridBar {
   unsigned nblocks;
   unsigned epoch;
   long long* trace;  // optional [nblocks][2*MEGA_TRACE_N]: arrival / release time of every barrier (BW_MEGA_TRACE=1)
-  // Two lessons from the timelines: (1) as a real (noinline) call the compiler waited for every in-flight prefetch load that
-  // is live across it (~1 us per phase); (2) the release fence of the arriving thread waits for that thread's OWN outstanding
-  // loads -- so the arriving thread is the CTA's last one, which never has a prefetch load in flight (it owns no LayerNorm
-  // slice for D <= 1280 and never finishes a row, see prefetch_phase).
-  // arrive() right after the CTA's own __syncthreads, wait() after whatever can be requested for the next phase: the arrival
-  // is not delayed by the prefetch issue, and the ~700 read requests of a slab copy queue behind the arrival, not before it
+  // the arriving thread is the CTA's last one: it never has a prefetch load in flight, so its release fence does not wait
+  // for one.  arrive() right after the CTA's own __syncthreads, wait() after whatever can be requested for the next phase.
   __device__ __forceinline__ void arrive() {
     if (threadIdx.x == MT - 1) {
       if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
       red_release_add(ctr, 1u);
     }
   }
-  // (a per-CTA flag array polled by one warp instead of the single counter was tried: 3+ us per barrier)
   __device__ __forceinline__ void wait() {
     if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
@@ -105,7 +93,7 @@ struct GridBar {
         const long long t0 = clock64();
         while (ld_acquire_u32(ctr) < target) {
           if (clock64() - t0 > (1ll << 32)) {
-            printf("[bw] decode_mega: grid barrier %u timed out (block %d)\n", epoch, blockIdx.x);
+            printf("[bw] decode_mega2: grid barrier %u timed out (block %d)\n", epoch, blockIdx.x);
             __trap();
           }
         }
@@ -236,8 +224,9 @@ __device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_
   } else {
     n = d.n0 + warp * d.R;
   }
-  const int r_sel = lane >> 3;
-  p.bias = (d.bias && (lane & 7) < 2 && r_sel < d.R && n + r_sel < d.nend) ? d.bias[n + r_sel] : 0.f;
+  // thread r finishes row n0 + r (the LM head has no bias)
+  p.bias = (!d.lm && d.bias && d.n0 + (int)threadIdx.x < d.nend) ? d.bias[d.n0 + threadIdx.x] : 0.f;
+  (void)n;
   const int k = threadIdx.x * 4;
   if (d.lng && k < d.K) {
     p.g = *reinterpret_cast<const float4*>(d.lng + k);
@@ -249,24 +238,14 @@ __device__ __forceinline__ void prefetch_phase(const GemvDesc& d, Pre& p, uint8_
 // The last warp takes no part in the staging: it runs `dma` (the TMA requests of the coming phases, ~0.25 us of issue
 // time) meanwhile and only joins the final CTA barrier.  The staging warps synchronise among themselves on named barrier 1.
 __device__ __forceinline__ void stage_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MT - 32) : "memory"); }
-// End of the staging: the staging warps synchronise among themselves and only SIGNAL the DMA warp (bar.arrive), which
-// waits for x (bar.sync on the same barrier) after it has issued its TMA requests -- the ~0.5 us of descriptor arithmetic
-// and TMA issue in `dma` run beside the dot products of the other warps instead of in front of them (r1_v8: the
-// K-parallel kernel, which has this property, gained 0.3 us on the phases without LayerNorm).
-__device__ __forceinline__ void stage_done_stagers() {
-  asm volatile("bar.sync 1, %0;" ::"n"(MT - 32) : "memory");
-  asm volatile("bar.arrive 3, %0;" ::"n"(MT) : "memory");
-}
-__device__ __forceinline__ void stage_done_dma() { asm volatile("bar.sync 3, %0;" ::"n"(MT) : "memory"); }
 
 template <int MB, class Dma>
-__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, bool split_end, Dma&& dma) {
+__device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, Dma&& dma) {
   const int K = d.K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == MW - 1) {
     dma();
-    if (split_end) stage_done_dma();
-    else __syncthreads();
+    __syncthreads();
     return;
   }
   constexpr int ST = MT - 32;  // staging threads
@@ -287,8 +266,7 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
         if (i < MB * K) *reinterpret_cast<float4*>(xs + i) = v[u];
       }
     }
-    if (split_end) stage_done_stagers();
-    else __syncthreads();
+    __syncthreads();
     return;
   }
   // LayerNorm (K <= 4 * ST): one float4 per thread and row, two-pass statistics through two reductions on register values
@@ -337,8 +315,137 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
       *reinterpret_cast<float4*>(xs + m * K + k) = o;
     }
   }
-  if (split_end) stage_done_stagers();
-  else __syncthreads();
+  __syncthreads();
+}
+
+// ---------------- K-parallel GEMV with x in registers (layer phases, one sequence) ----------------
+__device__ __forceinline__ void xsync() { asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory"); }
+
+// x -> registers of the XT compute threads (ld.global.cg), LayerNormed when the phase has one (then K <= XCH): the same
+// two-pass statistics, in the same summation order, as stage_x.
+__device__ __forceinline__ void load_x_regs(const GemvDesc& d, const Pre& p, float* red, float4 (&xr)[4]) {
+  const int K = d.K, k = threadIdx.x * 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int kk = c * XCH + k;
+    xr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < K) xr[c] = __ldcg(reinterpret_cast<const float4*>(d.src + kk));
+  }
+  if (!d.lng) return;
+  const bool have = k < K;
+  {
+    const float s = warp_sum((xr[0].x + xr[0].y) + (xr[0].z + xr[0].w));
+    if (lane == 0) red[warp] = s;
+  }
+  xsync();
+  float mean;
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < CW; ++w) s += red[w];
+    mean = s / (float)K;
+    float ss = 0.f;
+    if (have) {
+      const float a0 = xr[0].x - mean, a1 = xr[0].y - mean, a2 = xr[0].z - mean, a3 = xr[0].w - mean;
+      ss = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[16 + warp] = ss;
+  }
+  xsync();
+  {
+    float ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < CW; ++w) ss += red[16 + w];
+    const float rstd = rsqrtf(ss / (float)K + 1e-5f);
+    if (have) {
+      xr[0].x = (xr[0].x - mean) * rstd * p.g.x + p.b.x;
+      xr[0].y = (xr[0].y - mean) * rstd * p.g.y + p.b.y;
+      xr[0].z = (xr[0].z - mean) * rstd * p.g.z + p.b.z;
+      xr[0].w = (xr[0].w - mean) * rstd * p.g.w + p.b.w;
+    }
+  }
+}
+
+// v[j] = this lane's partial sum of row j (NV = 4, 16 or 32 rows).  Halving stages with masks 16, 8, ...: a lane keeps the
+// half of the rows selected by its own bit and hands the other half to its partner; the remaining stages are plain
+// xor-sums.  Afterwards every lane holds the warp total of row (lane >> (5 - log2 NV)).
+template <int NV>
+__device__ __forceinline__ float treduce(float (&v)[NV], int lane) {
+  int n = NV;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    if (n > 1) {
+      const int h = n >> 1;
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int j = 0; j < NV / 2; ++j) {
+        if (j < h) {
+          const float keep = up ? v[j + h] : v[j];
+          const float send = up ? v[j] : v[j + h];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+    }
+  }
+  return v[0];
+}
+
+// rows [r0, min(r0 + NV, rc)) of the CTA's slab ([rc][K] bf16) against this thread's x slice; the warp's totals go to
+// part_w[row] (this warp's line of the [CW][MAXRC] table).
+template <int NV>
+__device__ __forceinline__ void kdot(const uint8_t* slab, int K, int nch, int r0, int rc, const float4 (&xr)[4], float* part_w, int lane) {
+  float acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    const float4 x = c == 0 ? xr[0] : (c == 1 ? xr[1] : (c == 2 ? xr[2] : xr[3]));
+    const int kk = c * XCH + (int)threadIdx.x * 4;
+    if (kk < K) {
+      const uint8_t* wp = slab + ((size_t)r0 * K + kk) * 2;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (r0 + j < rc) {
+          const uint2 w = *reinterpret_cast<const uint2*>(wp + (size_t)j * K * 2);
+          const float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y);
+          float t = acc[j];
+          t = fmaf(a0.x, x.x, t);
+          t = fmaf(a0.y, x.y, t);
+          t = fmaf(a1.x, x.z, t);
+          t = fmaf(a1.y, x.w, t);
+          acc[j] = t;
+        }
+      }
+    }
+  }
+  const float tot = treduce<NV>(acc, lane);
+  constexpr int SH = NV == 32 ? 0 : (NV == 16 ? 1 : 3);
+  const int row = r0 + (lane >> SH);
+  if ((lane & ((1 << SH) - 1)) == 0 && row < rc) part_w[row] = tot;
+}
+
+// thread r finishes row n0 + r of a layer phase (one sequence): fold the CW warp partials in a fixed order, epilogue.
+__device__ __forceinline__ void finish_row(const GemvDesc& d, const float (*part)[MAXRC + 4], float bias, float res, int D, int Tmax, int pos) {
+  const int r = threadIdx.x;
+  const int nn = d.n0 + r;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < CW; ++w) v += part[w][r];
+  v += bias;
+  if (nn < d.alpha_cols) v *= d.alpha;
+  if (d.act == 1) v = gelu_erf(v);
+  if (d.residual) v += res;
+  d.out[nn] = v;
+  if (d.kc && nn >= D) {
+    const long long row = (long long)pos * D;
+    if (nn < 2 * D) d.kc[row + nn - D] = __float2bfloat16(v);
+    else d.vc[row + nn - 2 * D] = __float2bfloat16(v);
+  }
 }
 
 template <int MB, int R>
@@ -421,7 +528,7 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
 // red: [2][MW] floats, redo: [MW][64 + 8] floats.
 template <int NJ>
 __device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV, float* redo, float* red, const float (&qv)[8], int n,
-                                            float* score_out, float& mx_out, float& sum_out, float& ov_out, long long* mk = nullptr) {
+                                            float* score_out, float& mx_out, float& sum_out, float& ov_out) {
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // separate passes so that the NJ independent chains overlap: loads + FMAs of all keys, then the three shuffle stages
@@ -457,7 +564,6 @@ __device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV
     }
   }
   lmax = warp_max(lmax);
-  if (mk && threadIdx.x == 0) { mk[1] = global_ns(); mk[3] = clock64(); }
   if (lane == 0) red[warp] = lmax;
   __syncthreads();
   float mx = red[0];
@@ -521,8 +627,8 @@ __device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV
 }
 
 // smem carve-up (dynamic): red [64] | xs [MB*ffn] | pool: weight slabs from 0, attention scratch from ATT_OFF
-template <int MB>
-__global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
+__global__ void __launch_bounds__(MT, 1) decode_mega2_kernel(const __grid_constant__ MegaArgs a) {
+  constexpr int MB = 1;
   extern __shared__ __align__(128) uint8_t dyn[];
   float* red = reinterpret_cast<float*>(dyn);
   float* xs = red + 64;
@@ -532,7 +638,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t wbar[2 * MW];  // per warp: slab barrier (+ second stage for the LM head)
   __shared__ __align__(8) uint64_t xbar;          // cross-attention K/V item
   __shared__ __align__(8) uint64_t cbar[2];       // the CTA's weight slabs of a layer phase (one per slab region)
-  __shared__ long long wts[MW][2];                // trace only: per warp, slab landed / rows finished
+  __shared__ float part[CW][MAXRC + 4];           // per compute warp: its partial sum of every row of the CTA
   // the per-layer pointer table, copied out of the kernel parameter bank once: dynamically indexed constant loads at every
   // phase boundary missed the constant cache (it shares the 32 KB L1.5 with the instruction stream) -- ~1 us per phase
   __shared__ __align__(16) MegaLayer sl[MEGA_MAXL];
@@ -542,11 +648,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int D = a.D, H = a.H, Q = a.Q;
   const int pos = *a.pos;
   GridBar bar{a.bar, gridDim.x, 0u, a.trace};
-  const bool split_end = (a.flags & 64) != 0;  // the DMA warp does not hold up the end of the x staging
-  long long* const mkbase = a.trace ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + (long long)blockIdx.x * MEGA_TRACE_N * 4 : nullptr;
-  auto mark = [&](int j) {
-    if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) mkbase[bar.epoch * 4 + j] = global_ns();
-  };
 
   const int nsplit = a.nsplit;
   const int ks = (a.S + nsplit - 1) / nsplit;
@@ -592,16 +693,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   for (int ph = 0; ph < nph; ++ph) {
     const int l = ph / 6, g = ph - l * 6;
     const MegaLayer& L = sl[l];
-    // ---------------- GEMV phase g of layer l ----------------
+    // ---------------- GEMV phase g of layer l: K-parallel, x in registers ----------------
     {
-      const int n = cur.n0 + warp * cur.R;
-      const bool active = n < cur.nend;
+      const int rc = cur.nend - cur.n0;  // weight rows of this CTA in this phase (<= 0: none)
+      const int nch = (cur.K + XCH - 1) / XCH;
       float res = 0.f;
-      {
-        const int m = lane & 7, r_sel = lane >> 3;
-        if (cur.residual && active && r_sel < cur.R && m < MB && m < Q && n + r_sel < cur.nend)
-          res = __ldcg(cur.residual + (long long)m * cur.ldo + n + r_sel);
-      }
+      if (cur.residual && (int)threadIdx.x < rc) res = __ldcg(cur.residual + cur.n0 + threadIdx.x);
       auto ahead = [&]() {
       // two phases ahead, DRAM -> L2 (issued while the x loads of this phase are in flight, when the TMA queue is empty): a
         // layer is ~54 MB = 8 us of HBM time spread over ~35 us, but a 13 MB slab set requested only one barrier before its
@@ -627,37 +724,31 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
         }
       };
-      stage_x<MB>(xs, red, cur, pre, Q, split_end, ahead);
-      mark(2);
-      if (mkbase && lane == 0) wts[warp][0] = wts[warp][1] = 0;
-      if (active) {
-        mbar_wait(&cbar[ph & 1], (ph & 1) ? cpar1 : cpar0);
-        if (mkbase && lane == 0) wts[warp][0] = global_ns();
-        const uint8_t* slab = pool + ((ph & 1) ? 0 : a.p0_off) + (size_t)warp * cur.R * cur.K * 2;
-        float acc[3][MB];
-        if (cur.R == 3) dot_rows<MB, 3>(slab, xs, cur.K, acc, lane);
-        else if (cur.R == 2) dot_rows<MB, 2>(slab, xs, cur.K, acc, lane);
-        else dot_rows<MB, 1>(slab, xs, cur.K, acc, lane);
-        finish_rows<MB>(cur, acc, pre.bias, n, Q, res, true, D, a.Tmax, pos, lane);
-        if (mkbase && lane == 0) wts[warp][1] = global_ns();
+      if (warp == MW - 1) {
+        ahead();
+      } else if (warp < CW) {
+        float4 xr[4];
+        load_x_regs(cur, pre, red, xr);
+        if (rc > 0) {
+          mbar_wait(&cbar[ph & 1], (ph & 1) ? cpar1 : cpar0);
+          const uint8_t* slab = pool + ((ph & 1) ? 0 : a.p0_off);
+          if (rc <= 16) {
+            kdot<16>(slab, cur.K, nch, 0, rc, xr, part[warp], lane);
+          } else {
+            kdot<32>(slab, cur.K, nch, 0, rc, xr, part[warp], lane);
+            if (rc > 32) kdot<4>(slab, cur.K, nch, 32, rc, xr, part[warp], lane);
+          }
+        }
       }
-      mark(3);
-      if (cur.n0 < cur.nend) {  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
+      if (rc > 0) {  // (uniform per CTA: the phase's copy was issued iff the CTA owns rows)
         if (ph & 1) cpar1 ^= 1u;
         else cpar0 ^= 1u;
       }
+      __syncthreads();  // the partial sums are in smem and every read of the slab is done
+      if ((int)threadIdx.x < rc) finish_row(cur, part, pre.bias, res, D, a.Tmax, pos);
     }
-    __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
+    __syncthreads();  // the finishing threads' stores are ordered before the arrival
     bar.arrive();
-    if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
-      long long t0 = 0, t1 = 0;
-      for (int w = 0; w < MW; ++w) {
-        t0 = wts[w][0] > t0 ? wts[w][0] : t0;
-        t1 = wts[w][1] > t1 ? wts[w][1] : t1;
-      }
-      mkbase[bar.epoch * 4 + 0] = t0;
-      mkbase[bar.epoch * 4 + 1] = t1;
-    }
     cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6);
     if (!dbuf && !cur.lm) issue_slabs(cur, pool, &cbar[(ph + 1) & 1]);
     prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
@@ -751,11 +842,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           mbar_wait(&xbar, xpar);
           xpar ^= 1u;
-          mark(0);
-          if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) mkbase[bar.epoch * 4 + 2] = clock64();
           float mx, sum, ov;
-          attend_smem<(XKMAX + KG - 1) / KG>(sK, sV, redo, red, qv, n, align_row, mx, sum, ov,
-                                             (mkbase && bar.epoch < MEGA_TRACE_N) ? mkbase + bar.epoch * 4 : nullptr);
+          attend_smem<(XKMAX + KG - 1) / KG>(sK, sV, redo, red, qv, n, align_row, mx, sum, ov);
           const long long pb = ((long long)q * H + h) * nsplit + split;
           if (threadIdx.x < 64) a.part_o[pb * 64 + threadIdx.x] = ov;
           if (threadIdx.x == 0) {
@@ -809,7 +897,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   }
 
   // ---------------- final LayerNorm + tied LM head: row pairs, two slab stages per warp ----------------
-  stage_x<MB>(xs, red, cur, pre, Q, split_end, [] {});
+  stage_x<MB>(xs, red, cur, pre, Q, [] {});
   unsigned long long best = 0ull;  // of the logits this lane finished: (order-preserving value bits << 32) | ~token
   {
     const int K = cur.K, N = cur.N;
@@ -928,41 +1016,30 @@ size_t mega_smem_plan(int mb, int D, int ffn, int num_sms, bool want_dbuf, int* 
 
 }  // namespace
 
-// Launches the persistent step kernel on `st`.  Returns -3 when the configuration is outside what it supports
-// (the caller then uses the per-op path).
-int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
-  const int Q = a.Q;
-  if (a.L > MEGA_MAXL || Q > 2 || a.D > MAXD || a.ffn > 5120 || a.D % 8 != 0 || a.ffn % 8 != 0 || a.Tmax > MAXKEYS) return -3;
-  if ((size_t)MW * a.D * 2 > (size_t)ATT_OFF) return -3;  // R=1 slabs must stay below the attention scratch
-  const long long GW = (long long)num_sms * MW;
-  {  // every layer GEMV is one pass of at most 3 rows per warp
+// Launches the second-generation persistent step kernel on `st`.  Returns -3 when the configuration is outside what it
+// supports (more than one sequence, more than MAXRC rows per CTA and phase, ...): the caller then uses decode_mega.cu.
+int launch_decode_mega2(cudaStream_t st, const MegaArgs& a, int num_sms) {
+  if (a.Q != 1) return -3;
+  if (a.L > MEGA_MAXL || a.D > MAXD || a.ffn > 4 * XCH || a.D % 8 != 0 || a.ffn % 8 != 0 || a.Tmax > MAXKEYS) return -3;
+  if ((size_t)MW * a.D * 2 > (size_t)ATT_OFF) return -3;
+  {
     const int nmax = 3 * a.D > a.ffn ? 3 * a.D : a.ffn;
-    if (((nmax + num_sms - 1) / num_sms + MW - 1) / MW > 3) return -3;
+    if ((nmax + num_sms - 1) / num_sms > MAXRC) return -3;
   }
-  (void)GW;
   if (a.nsplit > XSPLIT) return -3;
-  const int mb = Q <= 1 ? 1 : 2;
   MegaArgs b = a;
-  const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
-  if (smem + 8 * 1024 > 227 * 1024) return -3;  // the 227 KB opt-in limit includes the static smem (layer table, barriers)
-  if ((size_t)((a.D + num_sms - 1) / num_sms) * a.D * 2 > (size_t)ATT_OFF) return -3;  // region-1 slabs live under the attention scratch
+  const size_t smem = mega_smem_plan(1, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
+  if (smem + 8 * 1024 > 227 * 1024) return -3;
+  if ((size_t)((a.D + num_sms - 1) / num_sms) * a.D * 2 > (size_t)ATT_OFF) return -3;
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
-#define BW_MEGA_CASE(MB)                                                                                              \
-  case MB: {                                                                                                          \
-    static size_t attr = 0;                                                                                           \
-    if (smem > attr) {                                                                                                \
-      BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr = smem;                                                                                                    \
-    }                                                                                                                 \
-    decode_mega_kernel<MB><<<num_sms, MT, smem, st>>>(b);                                                             \
-  } break;
-  switch (mb) {
-    BW_MEGA_CASE(1)
-    BW_MEGA_CASE(2)
+  static size_t attr = 0;
+  if (smem > attr) {
+    BW_CUDA_OK(cudaFuncSetAttribute(decode_mega2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
-#undef BW_MEGA_CASE
+  decode_mega2_kernel<<<num_sms, MT, smem, st>>>(b);
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }
