@@ -90,6 +90,9 @@ struct bw_engine {
   long long step_kernel_launches = 0;            // kernels launched by bw_decode_run so far (graph path)
   bool no_graph = false, simt = false, no_mega = false;
   int mega_flags = 0;  // BW_MEGA_FLAGS, re-read at every bw_decode_begin (each value has its own step graph)
+  int mega_variant = 0;  // BW_MEGA_VARIANT: compile-time variant of decode_mega_kernel (decode_mega.cu V_* bits)
+  unsigned long long* mega_ll = nullptr;  // self-validating activation words of the V_RELAXED variant
+  size_t mega_ll_words = 0;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
   long long* mega_trace = nullptr;
@@ -247,6 +250,9 @@ int step_impl(bw_engine* e, cudaStream_t st) {
       m.sel_best = e->sel_best; m.sel_ctr = e->sel_ctr;
     }
     m.flags = e->mega_flags;
+    m.variant = e->mega_variant;
+    m.ll = e->mega_ll;
+    m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
     int rc = -3;
     if (m.flags & 32) rc = launch_decode_mega2(st, m, e->num_sms);
     if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
@@ -516,6 +522,8 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
+  e->mega_ll_words = (size_t)2 * ((size_t)D + c.ffn) + 64;
+  if (dalloc(e, "mega_ll", &e->mega_ll, e->mega_ll_words)) return -1;
   if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] + per-CTA flags [32, 32 + SMs)
   {
     const char* tr = getenv("BW_MEGA_TRACE");
@@ -615,6 +623,7 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   BW_CUDA_OK(cudaMemsetAsync(e->pos, 0, sizeof(int), st));
   BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
   BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
+  BW_CUDA_OK(cudaMemsetAsync(e->mega_ll, 0, sizeof(unsigned long long) * e->mega_ll_words, st));  // tags restart with the position
   iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
@@ -622,12 +631,14 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   {  // experiment switches are re-read per decode so one process can A/B them (tools/mega_ab.py)
     const char* fl = getenv("BW_MEGA_FLAGS");
     e->mega_flags = fl ? atoi(fl) : MEGA_DEFAULT_FLAGS;
+    const char* vr = getenv("BW_MEGA_VARIANT");
+    e->mega_variant = vr ? atoi(vr) : 0;
     const char* nm = getenv("BW_NO_MEGA");
     e->no_mega = nm && nm[0] == '1';
   }
   if (!e->no_graph) {
     GraphKey key{A, G, opts->begin_index, opts->timestamp_rules * 4 + (opts->max_initial_timestamp_index + 1) * 8, opts->record_alignment,
-                 e->mega_flags * 4 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0)};
+                 e->mega_flags * 4 + e->mega_variant * 65536 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0)};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
       cudaStream_t cs;

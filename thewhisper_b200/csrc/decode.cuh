@@ -122,6 +122,9 @@ struct MegaArgs {
   unsigned long long* sel_best;  // [Q], zero between steps
   unsigned* sel_ctr;             // zero between steps
   int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
+  int variant;       // compile-time kernel variant (decode_mega.cu V_* bits; BW_MEGA_VARIANT), 0 = default
+  unsigned long long* ll;  // V_RELAXED: [2 * (D + ffn)] {tag, value} words: dx at 0, dh at ll_off_dh; zeroed by bw_decode_begin
+  int ll_off_dh;
 };
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).

@@ -42,6 +42,20 @@ constexpr int XKMAX = 256;     // cross-attention keys per work item held in sme
 constexpr int MAXD = 1280;
 constexpr int ATT_OFF = 32 * 1024;  // attention scratch starts here inside the pool (above the R=1 weight slabs)
 
+// Compile-time variants of the kernel (template parameter VAR, selected per launch by MegaArgs::variant / BW_MEGA_VARIANT).
+// VAR = 0 is the measured default; every other instantiation is a separate kernel, so a variant costs the default nothing
+// (dormant run-time branches did: +2.7 k instructions = +6 %, profiles/r1_v7_experiments.md).
+constexpr unsigned V_NOTRACE = 1;  // trace instrumentation compiled out
+constexpr unsigned V_RELAXED = 2;  // GEMV -> GEMV hand-overs (out-proj -> LN2+cross-q, cross out-proj -> LN3+fc1, fc1 -> fc2, fc2 -> next
+                                   // LN1+QKV / LM head): results travel as {tag, value} 64-bit words, the grid barrier in between
+                                   // has NO release / acquire (red.relaxed + ld.relaxed), the reader validates the tags
+                                   // (sync_bench test 12: 1385 ns against 1621 ns per hand-over)
+constexpr unsigned V_P2P = 4;      // the attention phases wait only for the CTAs that produce THEIR head's q / k / v rows (one
+                                   // counter per head) instead of a grid barrier after LN1+QKV and after LN2+cross-q
+constexpr int P2P_QKV = 256, P2P_XQ = 288;  // word offsets of the per-head counters inside MegaArgs::bar (1024 words, zeroed per launch;
+                                            // the sharded barrier counters live at words 0, 32, 64, 96)
+constexpr unsigned V_SHARD4 = 8;   // grid barrier counter sharded 4 ways (sync_bench: 1253 ns against 1316 ns)
+
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
   float2 t;
   t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
@@ -78,9 +92,62 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __noinline__ void wait_timeout(const char* what, unsigned a0, unsigned a1) {
+  printf("[bw] decode_mega: %s timed out (block %d thread %d: %u %u)\n", what, blockIdx.x, threadIdx.x, a0, a1);
+  __trap();
+}
+// ---- self-validating activations (V_RELAXED): one 64-bit word = {tag << 32 | fp32 bits}; 64-bit scalars are single-copy atomic
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// Reads N groups of four consecutive words (32-byte aligned) and re-reads until every tag is >= `tag` (after the relaxed
+// barrier the words are almost always there: 0 late words in 95 M reads of the microbenchmark).  Null groups are skipped.
+template <int N>
+__device__ __forceinline__ void ll_read4(const unsigned long long* const (&p)[N], unsigned tag, float4 (&out)[N]) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long w[N][4];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (p[i]) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][0]), "=l"(w[i][1]) : "l"(p[i]) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][2]), "=l"(w[i][3]) : "l"(p[i] + 2) : "memory");
+      } else {
+        w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0xffffffff00000000ull;
+      }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok = ok && ((unsigned)(w[i][j] >> 32) >= tag);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = p[i] ? make_float4(__uint_as_float((unsigned)w[i][0]), __uint_as_float((unsigned)w[i][1]), __uint_as_float((unsigned)w[i][2]),
+                                    __uint_as_float((unsigned)w[i][3]))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    if (clock64() - t0 > (1ll << 32)) wait_timeout("tagged activation read", tag, 0u);
+  }
+}
+
 // grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel).  bar.sync orders
 // the CTA's writes before thread 0's release; the acquire poll + bar.sync orders the other CTAs' writes before our reads.
+template <unsigned VAR>
 struct GridBar {
+  static constexpr bool TRACE = !(VAR & V_NOTRACE);
+  static constexpr bool SHARD = (VAR & V_SHARD4) != 0;
   unsigned* ctr;
   unsigned nblocks;
   unsigned epoch;
@@ -90,18 +157,39 @@ struct GridBar {
   // loads -- so the arriving thread is the CTA's last one, which never has a prefetch load in flight (it owns no LayerNorm
   // slice for D <= 1280 and never finishes a row, see prefetch_phase).
   // arrive() right after the CTA's own __syncthreads, wait() after whatever can be requested for the next phase: the arrival
-  // is not delayed by the prefetch issue, and the ~700 read requests of a slab copy queue behind the arrival, not before it
-  __device__ __forceinline__ void arrive() {
+  // is not delayed by the prefetch issue, and the ~700 read requests of a slab copy queue behind the arrival, not before it.
+  // relaxed = true (V_RELAXED hand-overs only): no release / acquire -- everything that crosses this barrier validates itself.
+  __device__ __forceinline__ void arrive(bool relaxed = false) {
     if (threadIdx.x == MT - 1) {
-      if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
-      red_release_add(ctr, 1u);
+      if (TRACE && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
+      unsigned* c = SHARD ? ctr + (blockIdx.x & 3u) * 32u : ctr;
+      if ((VAR & V_RELAXED) && relaxed) red_relaxed_add(c, 1u);
+      else red_release_add(c, 1u);
     }
   }
   // (a per-CTA flag array polled by one warp instead of the single counter was tried: 3+ us per barrier)
-  __device__ __forceinline__ void wait() {
-    if (threadIdx.x == MT - 1) {
+  __device__ __forceinline__ void wait(bool relaxed = false) {
+    if (SHARD) {
+      if (threadIdx.x >= MT - 4) {
+        const unsigned i = threadIdx.x - (MT - 4);
+        const unsigned cnt = (nblocks > i) ? (nblocks - i + 3u) >> 2 : 0u;  // CTAs b < nblocks with (b & 3) == i
+        const unsigned target = (epoch + 1) * cnt;
+        const long long t0 = clock64();
+        for (;;) {
+          const bool ok = (((VAR & V_RELAXED) && relaxed) ? ld_relaxed_u32(ctr + i * 32u) : ld_acquire_u32(ctr + i * 32u)) >= target;
+          if (__all_sync(0xf0000000u, ok)) break;
+          if (clock64() - t0 > (1ll << 32)) wait_timeout("sharded grid barrier", epoch, i);
+        }
+        if (TRACE && threadIdx.x == MT - 1 && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
+      }
+    } else if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
-      if (ld_acquire_u32(ctr) < target) {
+      if ((VAR & V_RELAXED) && relaxed) {
+        const long long t0 = clock64();
+        while (ld_relaxed_u32(ctr) < target) {
+          if (clock64() - t0 > (1ll << 32)) wait_timeout("relaxed grid barrier", epoch, 0u);
+        }
+      } else if (ld_acquire_u32(ctr) < target) {
         const long long t0 = clock64();
         while (ld_acquire_u32(ctr) < target) {
           if (clock64() - t0 > (1ll << 32)) {
@@ -110,7 +198,7 @@ struct GridBar {
           }
         }
       }
-      if (trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
+      if (TRACE && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
     }
     ++epoch;
     __syncthreads();
@@ -138,6 +226,10 @@ struct GemvDesc {
   float alpha;            // rows < alpha_cols are scaled (q * 1/sqrt(dh))
   int alpha_cols;
   bf16 *kc, *vc;          // optional self-KV append (fused QKV): rows [D, 2D) -> kc, [2D, 3D) -> vc at position pos
+  // V_RELAXED: where this phase reads its x / publishes its results as {tag, value} words (nullptr: plain fp32 + release barrier)
+  const unsigned long long* ll_in;
+  unsigned long long* ll_out;
+  unsigned tag_in, tag_out;
 };
 
 // g: 0 LN1+QKV | 1 self out-proj | 2 LN2+cross q | 3 cross out-proj | 4 LN3+fc1+GELU | 5 fc2; l == a.L: final LN + LM head
@@ -147,8 +239,26 @@ __device__ __forceinline__ void split_rows(GemvDesc& d) {
   d.n0 = min(d.N, (int)blockIdx.x * rc);
   d.nend = min(d.N, d.n0 + rc);
 }
-__device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g) {
+template <unsigned VAR>
+__device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g, int pos) {
   GemvDesc d;
+  d.ll_in = nullptr;
+  d.ll_out = nullptr;
+  d.tag_in = d.tag_out = 0u;
+  if (VAR & V_RELAXED) {
+    // tag = ((pos + 1) << 8) + producer phase + 1: strictly increasing within a decode (bw_decode_begin zeroes the words);
+    // phase index = 6 * layer + g, the LM head is phase 6 * L
+    const int ph = l * 6 + g;
+    const unsigned base = ((unsigned)pos + 1u) << 8;
+    d.tag_in = base + (unsigned)ph;  // = tag_out of phase ph - 1
+    d.tag_out = base + (unsigned)ph + 1u;
+    if (g == 2 || g == 4 || (g == 0 && l > 0)) d.ll_in = a.ll;  // dx published by out-proj / cross out-proj / fc2
+    if (g == 5) d.ll_in = a.ll + a.ll_off_dh;                    // dh published by fc1
+    if (l < a.L) {
+      if (g == 1 || g == 3 || g == 5) d.ll_out = a.ll;
+      if (g == 4) d.ll_out = a.ll + a.ll_off_dh;
+    }
+  }
   d.lng = d.lnb = nullptr;
   d.residual = nullptr;
   d.act = 0;
@@ -259,7 +369,7 @@ __device__ __forceinline__ void stage_done_stagers() {
 }
 __device__ __forceinline__ void stage_done_dma() { asm volatile("bar.sync 3, %0;" ::"n"(MT) : "memory"); }
 
-template <int MB, class Dma>
+template <int MB, unsigned VAR, class Dma>
 __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d, const Pre& p, int M, bool split_end, Dma&& dma) {
   const int K = d.K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -274,12 +384,23 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     constexpr int U = 4;
     for (int base = threadIdx.x * 4; base < MB * K; base += ST * 4 * U) {
       float4 v[U];
+      if ((VAR & V_RELAXED) && d.ll_in) {
+        const unsigned long long* pp[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = base + u * ST * 4;
-        const int m = (MB > 1 && i >= K) ? 1 : 0;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * ST * 4;
+          const int m = (MB > 1 && i >= K) ? 1 : 0;
+          pp[u] = (i < MB * K && m < M) ? d.ll_in + i : nullptr;
+        }
+        ll_read4<U>(pp, d.tag_in, v);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * ST * 4;
+          const int m = (MB > 1 && i >= K) ? 1 : 0;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -295,10 +416,17 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   const int k = threadIdx.x * 4;
   const bool have = k < K;
   float4 v[MB];
+  if ((VAR & V_RELAXED) && d.ll_in) {
+    const unsigned long long* pp[MB];
 #pragma unroll
-  for (int m = 0; m < MB; ++m) {
-    v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
+    for (int m = 0; m < MB; ++m) pp[m] = (have && m < M) ? d.ll_in + (long long)m * K + k : nullptr;
+    ll_read4<MB>(pp, d.tag_in, v);
+  } else {
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
+    }
   }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
@@ -388,7 +516,7 @@ __device__ __forceinline__ void dot_rows(const uint8_t* slab, const float* xs, i
 }
 
 // lanes [8r, 8r + MB) finish row n + r  (R <= 3, MB <= 8)
-template <int MB>
+template <int MB, unsigned VAR>
 __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc)[3][MB], float bias, int n, int M, float res,
                                             bool res_valid, int D, int Tmax, int pos, int lane) {
   const int m = lane & 7, r_sel = lane >> 3;
@@ -406,6 +534,7 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
     if (d.act == 1) v = gelu_erf(v);
     if (d.residual) v += res_valid ? res : __ldcg(d.residual + (long long)m * d.ldo + nn);
     d.out[(long long)m * d.ldo + nn] = v;
+    if ((VAR & V_RELAXED) && d.ll_out) ll_store(d.ll_out + (long long)m * d.ldo + nn, v, d.tag_out);
     if (d.kc && nn >= D) {
       const long long row = ((long long)m * Tmax + pos) * D;
       if (nn < 2 * D) d.kc[row + nn - D] = __float2bfloat16(v);
@@ -520,9 +649,40 @@ __device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV
   ov_out = ov;
 }
 
+// ---- V_P2P: per-head readiness counters instead of a grid barrier in front of the attention phases -------------------------
+// A CTA's rows [n0, nend) of a projection whose output is `nblk` blocks of D rows (QKV: q | k | v, cross-q: one block) touch
+// at most two 64-row head ranges (it owns fewer than 64 rows): it signals those heads.  Head h of layer l is ready when its
+// counter reaches (l + 1) * (number of CTAs whose rows intersect one of its ranges); the counters are zeroed with the
+// barrier words before every launch.
+__device__ __forceinline__ void p2p_signal(unsigned* ctr, int n0, int nend, int D) {
+  if (threadIdx.x == MT - 1 && n0 < nend) {
+    const int h0 = (n0 % D) >> 6, h1 = ((nend - 1) % D) >> 6;
+    red_release_add(ctr + h0, 1u);
+    if (h1 != h0) red_release_add(ctr + h1, 1u);
+  }
+}
+__device__ __forceinline__ unsigned p2p_expected(int h, int D, int nblk, int rc) {
+  unsigned n = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * D + h * 64;
+    n += (unsigned)((s0 + 63) / rc - s0 / rc + 1);
+  }
+  return n;
+}
+__device__ __forceinline__ void p2p_wait(const unsigned* ctr, unsigned target) {
+  if (threadIdx.x == MT - 1 && ld_acquire_u32(ctr) < target) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ctr) < target) {
+      if (clock64() - t0 > (1ll << 32)) wait_timeout("head readiness counter", target, ld_acquire_u32(ctr));
+    }
+  }
+  __syncthreads();
+}
+
 // smem carve-up (dynamic): red [64] | xs [MB*ffn] | pool: weight slabs from 0, attention scratch from ATT_OFF
-template <int MB>
+template <int MB, unsigned VAR>
 __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
+  constexpr bool TRACE = !(VAR & V_NOTRACE);
   extern __shared__ __align__(128) uint8_t dyn[];
   float* red = reinterpret_cast<float*>(dyn);
   float* xs = red + 64;
@@ -541,9 +701,9 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int gw = blockIdx.x * MW + warp, GW = gridDim.x * MW;
   const int D = a.D, H = a.H, Q = a.Q;
   const int pos = *a.pos;
-  GridBar bar{a.bar, gridDim.x, 0u, a.trace};
+  GridBar<VAR> bar{a.bar, gridDim.x, 0u, a.trace};
   const bool split_end = (a.flags & 64) != 0;  // the DMA warp does not hold up the end of the x staging
-  long long* const mkbase = a.trace ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + (long long)blockIdx.x * MEGA_TRACE_N * 4 : nullptr;
+  long long* const mkbase = (TRACE && a.trace) ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + (long long)blockIdx.x * MEGA_TRACE_N * 4 : nullptr;
   auto mark = [&](int j) {
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) mkbase[bar.epoch * 4 + j] = global_ns();
   };
@@ -569,7 +729,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   __syncthreads();
 
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
-  GemvDesc cur = make_desc(a, sl, 0, 0);
+  GemvDesc cur = make_desc<VAR>(a, sl, 0, 0, pos);
   Pre pre;
   // Slab regions: GEMV phase ph (= 6*layer + g) lives in region ph & 1 -- region 1 at the pool's start (out-proj, cross
   // out-proj, fc2), region 0 at p0_off (QKV, cross-q, fc1).  Double-buffered (p0_off > 0), the copy for phase ph + 1 is
@@ -607,12 +767,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         // layer is ~54 MB = 8 us of HBM time spread over ~35 us, but a 13 MB slab set requested only one barrier before its
         // use is still arriving when the phase starts, and the barrier's own atomics queue behind it
         if (dbuf && ph + 1 < nph) {
-          const GemvDesc d1 = make_desc(a, sl, (ph + 1) / 6, (ph + 1) % 6);
+          const GemvDesc d1 = make_desc<VAR>(a, sl, (ph + 1) / 6, (ph + 1) % 6, pos);
           issue_slabs(d1, pool + (((ph + 1) & 1) ? 0 : a.p0_off), &cbar[(ph + 1) & 1]);
         }
         if (!(a.flags & 1)) {
           if (ph + 2 <= nph) {
-            const GemvDesc d2 = make_desc(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6);
+            const GemvDesc d2 = make_desc<VAR>(a, sl, ph + 2 < nph ? (ph + 2) / 6 : a.L, (ph + 2) % 6, pos);
             l2_prefetch_phase(d2);
           }
           if (g == 0 && threadIdx.x == DMA_T + 1 && blockIdx.x < Q * H * nsplit) {  // this layer's cross-attention item
@@ -627,7 +787,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
         }
       };
-      stage_x<MB>(xs, red, cur, pre, Q, split_end, ahead);
+      stage_x<MB, VAR>(xs, red, cur, pre, Q, split_end, ahead);
       mark(2);
       if (mkbase && lane == 0) wts[warp][0] = wts[warp][1] = 0;
       if (active) {
@@ -638,7 +798,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (cur.R == 3) dot_rows<MB, 3>(slab, xs, cur.K, acc, lane);
         else if (cur.R == 2) dot_rows<MB, 2>(slab, xs, cur.K, acc, lane);
         else dot_rows<MB, 1>(slab, xs, cur.K, acc, lane);
-        finish_rows<MB>(cur, acc, pre.bias, n, Q, res, true, D, a.Tmax, pos, lane);
+        finish_rows<MB, VAR>(cur, acc, pre.bias, n, Q, res, true, D, a.Tmax, pos, lane);
         if (mkbase && lane == 0) wts[warp][1] = global_ns();
       }
       mark(3);
@@ -648,7 +808,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
-    bar.arrive();
+    // how this phase's results are handed over (decided before `cur` moves on to the next phase)
+    const bool relaxed_ho = (VAR & V_RELAXED) && cur.ll_out != nullptr;  // self-validating words: barrier without release / acquire
+    const bool p2p_ho = (VAR & V_P2P) && (g == 0 || g == 2);             // per-head counters: no grid barrier at all
+    unsigned* const p2p_ctr = a.bar + (g == 0 ? P2P_QKV : P2P_XQ);
+    if (p2p_ho) p2p_signal(p2p_ctr, cur.n0, cur.nend, D);
+    else bar.arrive(relaxed_ho);
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
       long long t0 = 0, t1 = 0;
       for (int w = 0; w < MW; ++w) {
@@ -658,7 +823,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       mkbase[bar.epoch * 4 + 0] = t0;
       mkbase[bar.epoch * 4 + 1] = t1;
     }
-    cur = make_desc(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6);
+    cur = make_desc<VAR>(a, sl, ph + 1 < nph ? (ph + 1) / 6 : a.L, (ph + 1) % 6, pos);
     if (!dbuf && !cur.lm) issue_slabs(cur, pool, &cbar[(ph + 1) & 1]);
     prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
 
@@ -674,10 +839,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
         }
       }
-      bar.wait();
+      if (!(VAR & V_P2P)) bar.wait();
       // ---------------- B: causal self-attention, one (sequence, head) per CTA ----------------
       for (int item = blockIdx.x; item < Q * H; item += gridDim.x) {
         const int q = item / H, h = item - q * H;
+        if (VAR & V_P2P) p2p_wait(a.bar + P2P_QKV + h, (unsigned)(l + 1) * p2p_expected(h, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
         const int n = pos + 1;
         uint8_t* sK = att;
         uint8_t* sV = att + (size_t)MAXKEYS * 128;
@@ -718,7 +884,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           bulk_g2s(att + XKMAX * 128, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
         }
       }
-      bar.wait();
+      if (!(VAR & V_P2P)) bar.wait();
       // ---------------- E: cross-attention, (audio, head, key split) items; last split of a head merges ----------------
       {
         uint8_t* sK = att;
@@ -737,6 +903,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
               bulk_g2s(sV, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
             }
           }
+          if (VAR & V_P2P) p2p_wait(a.bar + P2P_XQ + h, (unsigned)(l + 1) * p2p_expected(h, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
           float qv[8];
           {
             const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dq + (long long)q * D + h * 64 + sub * 8));
@@ -804,12 +971,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       bar.sync();
     } else {
-      bar.wait();
+      bar.wait(relaxed_ho);
     }
   }
 
   // ---------------- final LayerNorm + tied LM head: row pairs, two slab stages per warp ----------------
-  stage_x<MB>(xs, red, cur, pre, Q, split_end, [] {});
+  stage_x<MB, VAR>(xs, red, cur, pre, Q, split_end, [] {});
   unsigned long long best = 0ull;  // of the logits this lane finished: (order-preserving value bits << 32) | ~token
   {
     const int K = cur.K, N = cur.N;
@@ -832,7 +999,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
       float acc[3][MB];
       dot_rows<MB, 2>(pool + buf * set_bytes + (size_t)warp * slab_bytes, xs, K, acc, lane);
-      finish_rows<MB>(cur, acc, 0.f, n, Q, 0.f, true, D, a.Tmax, pos, lane);
+      finish_rows<MB, VAR>(cur, acc, 0.f, n, Q, 0.f, true, D, a.Tmax, pos, lane);
       if (a.fuse_select) {
         const int m = lane & 7, r_sel = lane >> 3, nn = n + r_sel;
         if (r_sel < 2 && m < MB && m < Q && nn < N) {
@@ -891,7 +1058,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
   }
-  if (a.trace && bar.epoch < MEGA_TRACE_N) {  // end of this CTA's LM-head share
+  if (TRACE && a.trace && bar.epoch < MEGA_TRACE_N) {  // end of this CTA's LM-head share
     __syncthreads();
     if (threadIdx.x == 0) a.trace[((long long)blockIdx.x * MEGA_TRACE_N + bar.epoch) * 2] = global_ns();
   }
@@ -941,6 +1108,8 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   }
   (void)GW;
   if (a.nsplit > XSPLIT) return -3;
+  if (a.variant != 0 && a.trace && (a.variant & (int)V_NOTRACE)) return -3;  // tracing needs the instrumented instantiation
+  if ((a.variant & (int)V_P2P) && (a.H > 32 || Q * a.H > num_sms)) return -3;
   const int mb = Q <= 1 ? 1 : 2;
   MegaArgs b = a;
   const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
@@ -949,20 +1118,33 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
-#define BW_MEGA_CASE(MB)                                                                                              \
-  case MB: {                                                                                                          \
-    static size_t attr = 0;                                                                                           \
-    if (smem > attr) {                                                                                                \
-      BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr = smem;                                                                                                    \
-    }                                                                                                                 \
-    decode_mega_kernel<MB><<<num_sms, MT, smem, st>>>(b);                                                             \
-  } break;
-  switch (mb) {
-    BW_MEGA_CASE(1)
-    BW_MEGA_CASE(2)
+  // MegaArgs::variant picks a compile-time variant (see V_* at the top); two sequences always run the default
+#define BW_MEGA_LAUNCH(MB, VAR)                                                                                            \
+  {                                                                                                                        \
+    static size_t attr = 0;                                                                                                \
+    if (smem > attr) {                                                                                                     \
+      BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr = smem;                                                                                                         \
+    }                                                                                                                      \
+    decode_mega_kernel<MB, VAR><<<num_sms, MT, smem, st>>>(b);                                                             \
   }
-#undef BW_MEGA_CASE
+  if (mb == 2) {
+    BW_MEGA_LAUNCH(2, 0u)
+  } else {
+    switch ((unsigned)a.variant) {
+      case 0u: BW_MEGA_LAUNCH(1, 0u) break;
+      case V_NOTRACE: BW_MEGA_LAUNCH(1, V_NOTRACE) break;
+      case V_NOTRACE | V_RELAXED: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED) break;
+      case V_NOTRACE | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_P2P) break;
+      case V_NOTRACE | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_SHARD4) break;
+      case V_NOTRACE | V_RELAXED | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P) break;
+      case V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4) break;
+      default:
+        set_error("decode_mega: variant %d is not instantiated", a.variant);
+        return -1;
+    }
+  }
+#undef BW_MEGA_LAUNCH
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }

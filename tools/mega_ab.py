@@ -1,6 +1,7 @@
-"""A/B of the persistent decoder-step kernel's experiment switches inside ONE process (large-v3 dims, random weights):
-BW_MEGA_FLAGS / BW_MEGA_REP are re-read at every decode_begin and each combination gets its own CUDA graph.
-Prints us/step per variant and checks that every variant reproduces variant 0's logits and tokens bit for bit."""
+"""A/B of the persistent decoder-step kernel's switches inside ONE process (large-v3 dims, random weights):
+BW_MEGA_FLAGS (run-time bits) and BW_MEGA_VARIANT (compile-time variant, decode_mega.cu V_* bits) are re-read at every
+decode_begin and each combination gets its own CUDA graph.  BW_AB="flags:variant,..." lists the combinations; the first
+is the reference the others' logits and tokens are compared with."""
 import os
 import sys
 
@@ -14,7 +15,7 @@ from tools.profile_decode import random_state_dict  # noqa: E402
 
 
 def main():
-    variants = [v for v in os.environ.get("BW_AB", "0:1,0:4,4:1,8:1,8:4,12:4,12:8").split(",") if v]
+    variants = [v for v in os.environ.get("BW_AB", "64:0,64:1,64:3,64:5,64:9,64:7,64:15,32:0").split(",") if v]
     A = int(os.environ.get("BW_A", "1"))
     dev = torch.device("cuda:0")
     dims = ModelDims.from_hf_config(S.make_hf_config(os.environ.get("BW_PRESET", "large-v3")))
@@ -32,7 +33,7 @@ def main():
     ref = None
     for v in variants:
         fl, nrep = v.split(":")
-        os.environ["BW_MEGA_FLAGS"], os.environ["BW_MEGA_REP"] = fl, nrep
+        os.environ["BW_MEGA_FLAGS"], os.environ["BW_MEGA_VARIANT"] = fl, nrep
         times = []
         for rep in range(4):
             eng.decode_begin(prompt, A, 1, opts)
@@ -50,7 +51,7 @@ def main():
             same = "reference"
         else:
             same = "tokens %s, logits max|d| %.3g" % ("equal" if np.array_equal(toks, ref[0]) else "DIFFER", float(np.abs(lg - ref[1]).max()))
-        print("flags %2s rep %s: %7.1f us/step (min), %7.1f (median)   pos %d   %s" % (fl, nrep, min(times[1:]), float(np.median(times[1:])), pos, same), flush=True)
+        print("flags %3s variant %2s: %7.1f us/step (min), %7.1f (median)   pos %d   %s" % (fl, nrep, min(times[1:]), float(np.median(times[1:])), pos, same), flush=True)
 
 
 if __name__ == "__main__":
