@@ -54,7 +54,11 @@ constexpr unsigned V_P2P = 4;      // the attention phases wait only for the CTA
                                    // counter per head) instead of a grid barrier after LN1+QKV and after LN2+cross-q
 constexpr int P2P_QKV = 256, P2P_XQ = 288;  // word offsets of the per-head counters inside MegaArgs::bar (1024 words, zeroed per launch;
                                             // the sharded barrier counters live at words 0, 32, 64, 96)
-constexpr unsigned V_SHARD4 = 8;   // grid barrier counter sharded 4 ways (sync_bench: 1253 ns against 1316 ns)
+constexpr unsigned V_SHARD4 = 8;
+constexpr unsigned V_PROD = 16;    // behind the attention phases only their PRODUCERS arrive (20 self-attention CTAs, the 20 CTAs that
+                                   // merged a head's cross-attention partials): one counter per phase kind, everybody polls it --
+                                   // 20 arrivals instead of 148 on the way into both out-projections
+constexpr int PROD_B = 320, PROD_E = 352;  // word offsets of those counters inside MegaArgs::bar   // grid barrier counter sharded 4 ways (sync_bench: 1253 ns against 1316 ns)
 
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
   float2 t;
@@ -868,8 +872,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (threadIdx.x < 64) a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / sum;
         fence_proxy_async_smem();  // this thread's scratch writes (generic proxy) before later TMA writes to the same bytes
         __syncthreads();
+        if ((VAR & V_PROD) && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_B, 1u);
       }
-      bar.sync();
+      if (VAR & V_PROD) p2p_wait(a.bar + PROD_B, (unsigned)(l + 1) * (unsigned)(Q * H));
+      else bar.sync();
     } else if (g == 2) {
       // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
       // (contiguous in the head-major cross cache: one bulk copy each)
@@ -967,9 +973,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           fence_proxy_async_smem();
           __syncthreads();
+          if ((VAR & V_PROD) && s_last && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_E, 1u);  // this CTA merged (q, h)
         }
       }
-      bar.sync();
+      if (VAR & V_PROD) p2p_wait(a.bar + PROD_E, (unsigned)(l + 1) * (unsigned)(Q * H));
+      else bar.sync();
     } else {
       bar.wait(relaxed_ho);
     }
@@ -1139,6 +1147,9 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
       case V_NOTRACE | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_SHARD4) break;
       case V_NOTRACE | V_RELAXED | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P) break;
       case V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4) break;
+      case V_NOTRACE | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_PROD) break;
+      case V_NOTRACE | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_P2P | V_PROD) break;
+      case V_NOTRACE | V_RELAXED | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_PROD) break;
       default:
         set_error("decode_mega: variant %d is not instantiated", a.variant);
         return -1;

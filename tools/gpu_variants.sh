@@ -5,8 +5,8 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD TRANSFORMERS_OFFLINE=1 HF_HUB_OFFLINE=1 TOKENIZERS_PARALLELISM=false
-BW_AB="64:0,64:1,64:3,64:5,64:9,64:7,64:15,32:0,64:0" timeout 600 python tools/mega_ab.py 2>&1 | tail -10 | tee gpurun_out/variants_ab.log
-for v in 3 5 7 15; do
+BW_AB="64:0,64:1,64:3,64:5,64:9,64:17,64:21,64:23,64:7,64:15,32:0,64:0" timeout 600 python tools/mega_ab.py 2>&1 | tail -13 | tee gpurun_out/variants_ab.log
+for v in 3 5 17 23 15; do
   echo "== variant $v: model parity tests"
   BW_MEGA_VARIANT=$v timeout 600 python -m pytest tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -k "teacher_forced or batch_rows" 2>&1 | grep -v Warning | tail -4 | tee gpurun_out/variants_tests_$v.log
 done
