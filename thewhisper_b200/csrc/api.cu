@@ -211,7 +211,10 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
 }
 
 // one decoder step for all Q sequences (enqueued on st; captured into a CUDA graph by the caller)
-int step_impl(bw_engine* e, cudaStream_t st) {
+// n_steps > 1 is honoured only by the V_MULTI variant of the persistent kernel (greedy selection fused, one sequence);
+// *done = how many steps were enqueued.
+int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullptr) {
+  if (done) *done = 1;
   const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, V = e->V, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
   const long long self_layer0 = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
   const long long cross_layer0 = (long long)e->cfg.max_audios * H * S * 64;
@@ -253,12 +256,14 @@ int step_impl(bw_engine* e, cudaStream_t st) {
     m.variant = e->mega_variant;
     m.ll = e->mega_ll;
     m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
+    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && !(m.flags & 32) && n_steps > 1) ? n_steps : 1;
     int rc = -3;
     if (m.flags & 32) rc = launch_decode_mega2(st, m, e->num_sms);
     if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;
       select_done = m.fuse_select != 0;
+      if (done) *done = m.n_steps;
     }
     else if (rc != -3) return rc;
   }
@@ -681,6 +686,17 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
 int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream) {
   BW_CHECK(e && e->finalized && e->Q > 0, "bw_decode_run: no decode in progress");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((e->mega_variant & 32) && !e->no_mega && e->G == 1 && e->Q == 1) {
+    // V_MULTI: up to 32 decoder steps per launch, enqueued directly (one memset + one kernel per chunk)
+    for (int i = 0; i < n_steps;) {
+      int done = 1;
+      const int want = n_steps - i < 32 ? n_steps - i : 32;
+      if (int rc = step_impl(e, st, want, &done)) return rc;
+      e->step_kernel_launches += 1;
+      i += done;
+    }
+    return 0;
+  }
   for (int i = 0; i < n_steps; ++i) {
     if (e->cur_graph) {
       BW_CUDA_OK(cudaGraphLaunch(e->cur_graph, st));

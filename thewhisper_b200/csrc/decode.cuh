@@ -123,6 +123,7 @@ struct MegaArgs {
   unsigned* sel_ctr;             // zero between steps
   int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
   int variant;       // compile-time kernel variant (decode_mega.cu V_* bits; BW_MEGA_VARIANT), 0 = default
+  int n_steps;       // decoder steps in this launch (> 1 only with the V_MULTI variant and fused selection)
   unsigned long long* ll;  // V_RELAXED: [2 * (D + ffn)] {tag, value} words: dx at 0, dh at ll_off_dh; zeroed by bw_decode_begin
   int ll_off_dh;
 };

@@ -58,6 +58,8 @@ constexpr unsigned V_SHARD4 = 8;
 constexpr unsigned V_PROD = 16;    // behind the attention phases only their PRODUCERS arrive (20 self-attention CTAs, the 20 CTAs that
                                    // merged a head's cross-attention partials): one counter per phase kind, everybody polls it --
                                    // 20 arrivals instead of 148 on the way into both out-projections
+constexpr unsigned V_MULTI = 32;   // MegaArgs::n_steps decoder steps per launch (greedy selection fused): the token and the position travel through
+                                   // global memory behind one extra grid barrier per step; no launch gap, no memset node, no prologue per token
 constexpr int PROD_B = 320, PROD_E = 352;  // word offsets of those counters inside MegaArgs::bar   // grid barrier counter sharded 4 ways (sync_bench: 1253 ns against 1316 ns)
 
 __device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * MW + warp, GW = gridDim.x * MW;
   const int D = a.D, H = a.H, Q = a.Q;
-  const int pos = *a.pos;
+  const int pos0 = *a.pos;
   GridBar<VAR> bar{a.bar, gridDim.x, 0u, a.trace};
   const bool split_end = (a.flags & 64) != 0;  // the DMA warp does not hold up the end of the x staging
   long long* const mkbase = (TRACE && a.trace) ? a.trace + (long long)gridDim.x * MEGA_TRACE_N * 2 + (long long)blockIdx.x * MEGA_TRACE_N * 4 : nullptr;
@@ -732,6 +734,12 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   }
   __syncthreads();
 
+  const int nsteps = (VAR & V_MULTI) ? a.n_steps : 1;
+  for (int step = 0; step < nsteps; ++step) {
+  // (V_MULTI: the previous step's last CTA wrote the token and advanced the position before it arrived at the barrier that
+  // ends a step, so both are read from L2 here)
+  const int pos = ((VAR & V_MULTI) && step > 0) ? __ldcg(a.pos) : pos0;
+  const int lbase = step * a.L;  // the per-head / per-phase-kind counters count layers across the steps of a launch
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   GemvDesc cur = make_desc<VAR>(a, sl, 0, 0, pos);
   Pre pre;
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
-      const int tok = a.tokens[q * a.Tmax + pos];
+      const int tok = (VAR & V_MULTI) ? __ldcg(a.tokens + q * a.Tmax + pos) : a.tokens[q * a.Tmax + pos];
       a.dx[i] = __bfloat162float(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
     }
   }
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       // ---------------- B: causal self-attention, one (sequence, head) per CTA ----------------
       for (int item = blockIdx.x; item < Q * H; item += gridDim.x) {
         const int q = item / H, h = item - q * H;
-        if (VAR & V_P2P) p2p_wait(a.bar + P2P_QKV + h, (unsigned)(l + 1) * p2p_expected(h, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
+        if (VAR & V_P2P) p2p_wait(a.bar + P2P_QKV + h, (unsigned)(lbase + l + 1) * p2p_expected(h, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
         const int n = pos + 1;
         uint8_t* sK = att;
         uint8_t* sV = att + (size_t)MAXKEYS * 128;
@@ -874,7 +882,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         __syncthreads();
         if ((VAR & V_PROD) && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_B, 1u);
       }
-      if (VAR & V_PROD) p2p_wait(a.bar + PROD_B, (unsigned)(l + 1) * (unsigned)(Q * H));
+      if (VAR & V_PROD) p2p_wait(a.bar + PROD_B, (unsigned)(lbase + l + 1) * (unsigned)(Q * H));
       else bar.sync();
     } else if (g == 2) {
       // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
@@ -909,7 +917,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
               bulk_g2s(sV, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
             }
           }
-          if (VAR & V_P2P) p2p_wait(a.bar + P2P_XQ + h, (unsigned)(l + 1) * p2p_expected(h, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
+          if (VAR & V_P2P) p2p_wait(a.bar + P2P_XQ + h, (unsigned)(lbase + l + 1) * p2p_expected(h, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
           float qv[8];
           {
             const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dq + (long long)q * D + h * 64 + sub * 8));
@@ -976,7 +984,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           if ((VAR & V_PROD) && s_last && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_E, 1u);  // this CTA merged (q, h)
         }
       }
-      if (VAR & V_PROD) p2p_wait(a.bar + PROD_E, (unsigned)(l + 1) * (unsigned)(Q * H));
+      if (VAR & V_PROD) p2p_wait(a.bar + PROD_E, (unsigned)(lbase + l + 1) * (unsigned)(Q * H));
       else bar.sync();
     } else {
       bar.wait(relaxed_ho);
@@ -1066,6 +1074,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
   }
+  if ((VAR & V_MULTI) && step + 1 < nsteps) bar.sync();  // the token and the position of the next step are in global memory
+  }  // step
   if (TRACE && a.trace && bar.epoch < MEGA_TRACE_N) {  // end of this CTA's LM-head share
     __syncthreads();
     if (threadIdx.x == 0) a.trace[((long long)blockIdx.x * MEGA_TRACE_N + bar.epoch) * 2] = global_ns();
@@ -1118,6 +1128,7 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   if (a.nsplit > XSPLIT) return -3;
   if (a.variant != 0 && a.trace && (a.variant & (int)V_NOTRACE)) return -3;  // tracing needs the instrumented instantiation
   if ((a.variant & (int)V_P2P) && (a.H > 32 || Q * a.H > num_sms)) return -3;
+  if (a.n_steps > 1 && !((a.variant & (int)V_MULTI) && a.fuse_select && Q <= 1)) return -3;  // several steps per launch: V_MULTI only
   const int mb = Q <= 1 ? 1 : 2;
   MegaArgs b = a;
   const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
@@ -1147,6 +1158,8 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
       case V_NOTRACE | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_SHARD4) break;
       case V_NOTRACE | V_RELAXED | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P) break;
       case V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4) break;
+      case V_NOTRACE | V_MULTI: BW_MEGA_LAUNCH(1, V_NOTRACE | V_MULTI) break;
+      case V_NOTRACE | V_RELAXED | V_P2P | V_PROD | V_MULTI: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_PROD | V_MULTI) break;
       case V_NOTRACE | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_PROD) break;
       case V_NOTRACE | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_P2P | V_PROD) break;
       case V_NOTRACE | V_RELAXED | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_PROD) break;
