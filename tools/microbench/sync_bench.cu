@@ -276,6 +276,100 @@ __global__ void __launch_bounds__(MT, 1) k_hint(Args a) {
   if (acc == 123.456f) a.sink[0] = acc;
 }
 
+// test 13: partial barrier -- only `nprod` CTAs arrive (red.release), every CTA polls (what stands between an attention phase
+// with 20 producer CTAs and the out-projection that needs all heads).  test 14: point-to-point -- 20 counters, counter h gets
+// 8 arrivals (the CTAs that produce head h's rows) and is polled by 7 CTAs (the key splits of head h); the other CTAs idle.
+__global__ void __launch_bounds__(MT, 1) k_partial(Args a) {
+  extern __shared__ unsigned char dyn[];
+  unsigned epoch = 0;
+  grid_barrier(a.ctr + 1024 - 32, epoch, 0);
+  const long long t0 = gns();
+  for (int it = 0; it < a.rounds; ++it) {
+    __syncthreads();
+    if (a.mode == 13) {
+      const int nprod = 20;
+      if (threadIdx.x == MT - 1) {
+        if ((int)blockIdx.x < nprod) red_release(a.ctr, 1u);
+        const unsigned target = (unsigned)(it + 1) * nprod;
+        const long long tt = clock64();
+        while (ld_acquire(a.ctr) < target) guard(tt, 13);
+      }
+    } else {
+      // producers: CTA b signals head (b * 20 / gridDim) -- about gridDim/20 arrivals per head; pollers: CTA b < 140 polls head b / 7
+      const int H = 20;
+      const int hp = (int)((long long)blockIdx.x * H / gridDim.x);
+      if (threadIdx.x == MT - 1) {
+        red_release(a.ctr + 32 * hp, 1u);
+        if ((int)blockIdx.x < H * 7) {
+          const int hc = blockIdx.x / 7;
+          unsigned cnt = 0;
+          for (int b = 0; b < (int)gridDim.x; ++b) cnt += ((int)((long long)b * H / gridDim.x) == hc);
+          const unsigned target = (unsigned)(it + 1) * cnt;
+          const long long tt = clock64();
+          while (ld_acquire(a.ctr + 32 * hc) < target) guard(tt, 14);
+        }
+      }
+      // (a full barrier every 64 rounds keeps the non-polling CTAs from running ahead without bound)
+      if ((it & 63) == 63) grid_barrier(a.ctr + 1024 - 32, epoch, 0);
+    }
+    __syncthreads();
+  }
+  const long long t1 = gns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.out_ns[0] = t1 - t0;
+}
+
+// test 16: fp32 reductions through L2: 140 CTAs each add 64 partial values into each of ... -- the pattern of an out-projection
+// fused into the attention phase: CTA (h, j) adds its 183-row slice of head h's contribution: 1280 addresses x 20 contributions.
+// Reports ns per round including the grid barrier that follows (compare with test 0).
+__global__ void __launch_bounds__(MT, 1) k_redf32(Args a) {
+  extern __shared__ unsigned char dyn[];
+  unsigned epoch = 0;
+  grid_barrier(a.ctr, epoch, 0);
+  const long long t0 = gns();
+  for (int it = 0; it < a.rounds; ++it) {
+    if (blockIdx.x < 140) {
+      const int j = blockIdx.x % 7;          // row slice of this CTA
+      const int r0 = j * 183;
+      for (int r = threadIdx.x; r < 183 && r0 + r < NV; r += MT) atomicAdd(a.x + (it & 1) * NV + r0 + r, 1.0f);
+    }
+    grid_barrier(a.ctr, epoch, 0);
+  }
+  const long long t1 = gns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.out_ns[0] = t1 - t0;
+}
+
+// test 15: hand-over inside a thread-block cluster through distributed shared memory: every CTA writes 16 floats into the smem
+// of every CTA of its cluster (st.shared::cluster), then barrier.cluster arrive.release / wait.acquire; ns per round.
+template <int CS>
+__global__ void __launch_bounds__(MT, 1) k_cluster(Args a) {
+  __shared__ float box[8][16];
+  unsigned rank, nctas;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nctas));
+  float acc = 0.f;
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const long long t0 = gns();
+  for (int it = 0; it < a.rounds; ++it) {
+    if (threadIdx.x < 16 * nctas) {
+      const unsigned dst = threadIdx.x / 16, i = threadIdx.x % 16;
+      unsigned local = (unsigned)__cvta_generic_to_shared(&box[rank][i]);
+      unsigned remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(dst));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(acc + (float)it) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 16 * nctas) acc += box[threadIdx.x / 16][threadIdx.x % 16] * 1e-9f;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  const long long t1 = gns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.out_ns[0] = t1 - t0;
+  if (acc == 123.456f) a.sink[0] = acc;
+}
+
+__global__ void k_empty(Args a) {
+  if (a.rounds == -1) a.sink[0] = 1.f;
+}
+
 int main() {
   int dev = 0, sms = 0, khz = 0;
   CK(cudaSetDevice(dev));
@@ -293,6 +387,7 @@ int main() {
   const int smem = 200 * 1024;
   CK(cudaFuncSetAttribute(k_barrier, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_empty, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const char* names[] = {"grid barrier (red.release + ld.acquire poll)", "grid barrier (__threadfence + red.relaxed)",
                          "barrier + all-to-all of 1280 floats (write share, barrier, every CTA reads 5 KB)",
                          "flag-in-data all-to-all, 320 pollers per CTA spinning", "flag-in-data all-to-all, pollers with nanosleep(40)",
@@ -335,6 +430,91 @@ int main() {
                            mode >= 11 ? (ns[2] ? "  [some words were late: re-polled]" : "  [no re-polls]") : "");
       if (rep == 1 && mode >= 11) printf("         late-word re-polls: %lld over %d rounds x %d threads\n", ns[2], a.rounds, sms * XT);
     }
+  }
+  CK(cudaFuncSetAttribute(k_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_redf32, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int mode : {13, 14, 16}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      a.mode = mode;
+      a.rounds = 2000;
+      CK(cudaMemset(a.ctr, 0, 4096));
+      CK(cudaMemset(a.x, 0, 2 * NV * sizeof(float)));
+      if (mode == 16) k_redf32<<<sms, MT, smem>>>(a);
+      else k_partial<<<sms, MT, smem>>>(a);
+      CK(cudaGetLastError());
+      CK(cudaDeviceSynchronize());
+      long long ns = 0;
+      CK(cudaMemcpy(&ns, a.out_ns, 8, cudaMemcpyDeviceToHost));
+      if (rep == 1)
+        printf("test %d: %7.1f ns / round   %s\n", mode, (double)ns / a.rounds,
+               mode == 13 ? "partial barrier: 20 CTAs arrive, all 148 poll"
+                          : (mode == 14 ? "point-to-point: 20 counters, ~7 arrivals and 7 pollers each"
+                                        : "25.6 k fp32 atomicAdd into 1280 addresses (20 per address) + grid barrier"));
+    }
+  }
+  {  // test 15: cluster hand-over through DSMEM
+    a.rounds = 2000;
+    auto run_cluster = [&](int cs) {
+      cudaLaunchConfig_t cfg = {};
+      const int grid = sms / cs * cs;
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(MT);
+      cfg.dynamicSmemBytes = 0;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaSuccess;
+      for (int rep = 0; rep < 2 && e == cudaSuccess; ++rep) {
+        if (cs == 2) e = cudaLaunchKernelEx(&cfg, k_cluster<2>, a);
+        else if (cs == 4) e = cudaLaunchKernelEx(&cfg, k_cluster<4>, a);
+        else e = cudaLaunchKernelEx(&cfg, k_cluster<8>, a);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      }
+      if (e != cudaSuccess) { printf("test 15: cluster size %d: %s\n", cs, cudaGetErrorString(e)); cudaGetLastError(); return; }
+      long long ns = 0;
+      CK(cudaMemcpy(&ns, a.out_ns, 8, cudaMemcpyDeviceToHost));
+      printf("test 15: %7.1f ns / round   cluster of %d: DSMEM all-to-all of 16 floats + 2 cluster barriers (grid %d)\n", (double)ns / a.rounds, cs, grid);
+    };
+    run_cluster(2);
+    run_cluster(4);
+    run_cluster(8);
+  }
+  {  // test 17: what a launch boundary costs: back-to-back launches of an empty kernel, and of a memset + kernel graph
+    a.rounds = 0;
+    cudaStream_t st;
+    CK(cudaStreamCreate(&st));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int n = 2000;
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaEventRecord(e0, st));
+      for (int i = 0; i < n; ++i) k_empty<<<sms, MT, 0, st>>>(a);
+      CK(cudaEventRecord(e1, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("test 17: %7.2f us per back-to-back launch of an empty %d x %d kernel\n", ms * 1e3 / n, sms, MT);
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    CK(cudaMemsetAsync(a.ctr, 0, 4096, st));
+    k_empty<<<sms, MT, smem, st>>>(a);
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaEventRecord(e0, st));
+      for (int i = 0; i < n; ++i) CK(cudaGraphLaunch(ge, st));
+      CK(cudaEventRecord(e1, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("test 17: %7.2f us per launch of a (4 KB memset + empty kernel with 200 KB smem) graph -- the per-token boundary of the decoder\n", ms * 1e3 / n);
   }
   for (int grid : {2, sms}) {
     a.rounds = 2000;
