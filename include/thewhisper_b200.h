@@ -108,6 +108,14 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision,
                        float* out_host, void* stream);
 
+/* ---- host-side post-processing (no CUDA) ---------------------------------------------------------------------- */
+/* Seam merge of overlapping chunks: the reference's patched `_find_longest_common_sequence`
+ * (REF thestage_speechkit/__init__.py:5-134, installed at :137-139).  tokens: the n_seq sequences concatenated, lens[n_seq];
+ * ts: NULL, or one (start, end) pair of doubles per token (NaN = Python None); out_tokens / out_ts sized for the sum of
+ * lens.  Returns 0, or -3 where Python would raise TypeError (a float end compared with None). */
+int bw_host_merge_overlapping(const int32_t* tokens, const int32_t* lens, int32_t n_seq, const double* ts,
+                              int32_t* out_tokens, double* out_ts, int32_t* out_len);
+
 /* ---- single-op entry points (used by the parity tests; same kernels as the engine) --------------------------- */
 /* C[M,N] = epi(A[M,K] W[N,K]^T): impl 0 = tcgen05, 1 = CUDA-core comparator.  out_is_f32 selects the output type. */
 int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,

@@ -57,6 +57,49 @@ def test_lcs_golden():
                 assert fn(c["seqs"]) == c["out"]
 
 
+def test_native_seam_merge_matches_oracle_on_random_cases():
+    """csrc/hostproc.cu (the product's seam merge, through the C-ABI) against the oracle restatement of the reference's
+    `_find_longest_common_sequence` on random overlapping chunks: plain, with token timestamps, with open-ended (None)
+    entries, and the TypeError the reference raises when a float end meets None."""
+    from oracle import hf_ref
+    from thewhisper_b200.hostproc import merge_overlapping
+
+    rng = np.random.RandomState(7)
+    for trial in range(200):
+        n_seq = int(rng.randint(1, 5))
+        base = rng.randint(0, 12, size=400).tolist()  # small alphabet: many accidental matches
+        seqs, tss, p = [], [], 0
+        for k in range(n_seq):
+            ln = int(rng.randint(0, 40))
+            seq = base[p:p + ln]
+            if rng.rand() < 0.5 and ln:
+                seq = [int(t) if rng.rand() > 0.1 else int(rng.randint(0, 12)) for t in seq]
+            seqs.append(seq)
+            t0 = p * 0.02 + rng.rand() * 0.1
+            ts = [(round(t0 + 0.02 * j, 2), round(t0 + 0.02 * j + 0.02, 2)) for j in range(ln)]
+            if trial % 3 == 2 and ln:  # open-ended left entries (always count) -- never on the right-hand side of a <=
+                j = int(rng.randint(0, ln))
+                if k == 0:
+                    ts[j] = (ts[j][0], None)
+            tss.append(ts)
+            p += max(0, ln - int(rng.randint(0, 12)))
+        assert merge_overlapping(seqs) == hf_ref.lcs_merge(seqs)
+        if n_seq and all(len(s) for s in seqs):
+            try:
+                want = hf_ref.lcs_merge(seqs, tss)
+            except TypeError:
+                with pytest.raises(TypeError):
+                    merge_overlapping(seqs, tss)
+                continue
+            got = merge_overlapping(seqs, tss)
+            assert got[0] == want[0] and list(got[1]) == list(want[1]), trial
+    # float end against None on the right: Python raises, so does the native path
+    with pytest.raises(TypeError):
+        hf_ref.lcs_merge([[1, 2, 3], [1, 2, 3]], [[(0.0, 0.1), (0.1, 0.2), (0.2, 0.3)], [(0.0, None), (0.1, None), (0.2, None)]])
+    with pytest.raises(TypeError):
+        merge_overlapping([[1, 2, 3], [1, 2, 3]], [[(0.0, 0.1), (0.1, 0.2), (0.2, 0.3)], [(0.0, None), (0.1, None), (0.2, None)]])
+
+
 def test_logits_rules_match_transformers():
     from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
                                                         WhisperTimeStampLogitsProcessor)

@@ -59,6 +59,7 @@ SYMBOLS = {
     "bw_decode_reorder": (C.c_int, [_P, _P, _P, _P]),
     "bw_decode_beam_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "bw_word_timestamps": (C.c_int, [_P, _I, _I, _I, _F, _P, _P]),
+    "bw_host_merge_overlapping": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
     "bw_op_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _I, _I, _I, _P]),
     "bw_op_attn_enc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "bw_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),

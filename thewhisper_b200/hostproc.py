@@ -1,6 +1,6 @@
 """Host-side pre/post-processing around the engine: chunk windows and the seam merge of overlapping chunks.
 
-`merge_overlapping` implements the reference's patched token-level longest-common-sequence merge
+`merge_overlapping` is the reference's patched token-level longest-common-sequence merge
 (REF thestage_speechkit/__init__.py:5-134, installed over transformers' at :137-139): slide the right chunk's
 tokens over the left chunk's, score each overlap by matches/len + len/10000, require more than one match, and with
 word timestamps only count matches whose left time <= right time (a left entry with an open end always counts,
@@ -13,55 +13,47 @@ from typing import Iterator, List, Optional, Sequence, Tuple
 import numpy as np
 
 
-def _ts_le(a, b) -> bool:
-    """The reference's compare(): open-ended left timestamps always pass, otherwise tuple order."""
-    if a[1] is None:
-        return True
-    return a <= b
-
-
 def merge_overlapping(sequences: Sequence[Sequence[int]], token_timestamp_sequences=None):
+    """Drop-in for `_find_longest_common_sequence` (same arguments, same return shapes).  The arithmetic runs in the native
+    library (csrc/hostproc.cu: bw_host_merge_overlapping); this wrapper only marshals Python lists."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
     with_ts = bool(token_timestamp_sequences)
-    left = np.asarray(sequences[0], dtype=np.int64)
-    merged: List[int] = []
+    lens = np.asarray([len(s) for s in sequences], dtype=np.int32)
+    total = int(lens.sum())
+    toks = np.zeros(max(total, 1), dtype=np.int32)
+    if total:
+        toks[:total] = np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in sequences]).astype(np.int32)
+    ts = None
     if with_ts:
-        left_ts = list(token_timestamp_sequences[0])
-        merged_ts: list = []
-    for k in range(1, len(sequences)):
-        right = np.asarray(sequences[k], dtype=np.int64)
-        right_ts = token_timestamp_sequences[k] if with_ts else None
-        nl, nr = len(left), len(right)
-        best_score, best = 0.0, (nl, nl, 0, 0)
-        for shift in range(1, nl + nr):
-            l0, l1 = max(0, nl - shift), min(nl, nl + nr - shift)
-            r0, r1 = max(0, shift - nl), min(nr, shift)
-            if l1 - l0 != r1 - r0:
-                raise RuntimeError("There is a bug within whisper `decode_asr` function, please report it. "
-                                   "Dropping to prevent bad inference.")
-            eq = left[l0:l1] == right[r0:r1]
-            if with_ts:
-                hits = 0
-                for j in np.nonzero(eq)[0]:
-                    if _ts_le(left_ts[l0 + j], right_ts[r0 + j]):
-                        hits += 1
-            else:
-                hits = int(eq.sum())
-            score = hits / shift + shift / 10000.0
-            if hits > 1 and score > best_score:
-                best_score, best = score, (l0, l1, r0, r1)
-        l0, l1, r0, r1 = best
-        cut_l, cut_r = (l0 + l1) // 2, (r0 + r1) // 2
-        merged.extend(left[:cut_l].tolist())
-        left = right[cut_r:]
-        if with_ts:
-            merged_ts.extend(left_ts[:cut_l])
-            left_ts = list(right_ts[cut_r:])
-    merged.extend(left.tolist())
+        ts = np.full((max(total, 1), 2), np.nan, dtype=np.float64)
+        i = 0
+        for seq in token_timestamp_sequences:
+            for t in seq:
+                ts[i, 0] = t[0]
+                if t[1] is not None:
+                    ts[i, 1] = t[1]
+                i += 1
+        if i != total:
+            raise ValueError("token_timestamp_sequences must have one (start, end) entry per token")
+    out = np.zeros(max(total, 1), dtype=np.int32)
+    out_ts = np.zeros((max(total, 1), 2), dtype=np.float64) if with_ts else None
+    n = C.c_int32(0)
+    rc = lib.bw_host_merge_overlapping(toks.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), len(sequences),
+                                       ts.ctypes.data_as(C.c_void_p) if with_ts else None, out.ctypes.data_as(C.c_void_p),
+                                       out_ts.ctypes.data_as(C.c_void_p) if with_ts else None, C.byref(n))
+    if rc == -3:
+        raise TypeError("'<=' not supported between instances of 'float' and 'NoneType'")
+    if rc != 0:
+        raise RuntimeError((lib.bw_last_error() or b"bw_host_merge_overlapping failed").decode("utf-8", "replace"))
+    merged = out[: n.value].tolist()
     if token_timestamp_sequences is None:
         return merged
     if len(token_timestamp_sequences) > 0:
-        merged_ts.extend(left_ts)
-        return merged, merged_ts
+        return merged, [(x, None if np.isnan(y) else y) for x, y in out_ts[: n.value].tolist()]
     return merged, []
 
 
