@@ -90,6 +90,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of one decoder-step kernel launch from the committed `ncu --set full` capture (profiles/*_mega_ncu_raw.csv:
+    dram__bytes_read.sum + dram__bytes_write.sum) -- a measurement taken under the profiler, reported beside the live
+    CUDA-event numbers, never instead of them.  None when no capture is committed."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_mega_ncu_raw.csv")))
+    if not files:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = 0.0
+    for row in csv.reader(open(files[-1])):
+        if len(row) == 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * scale.get(row[1], 1.0)
+    return (tot or None), os.path.relpath(files[-1], ROOT)
+
+
 def decode_bytes_per_step(dims, S: int, A: int, t_mean: float) -> float:
     """Algorithmic HBM bytes of one decoder step: weights + A * cross-KV + A * self-KV(t)."""
     d, L, V, ffn = dims.d_model, dims.dec_layers, dims.vocab, dims.ffn
@@ -271,6 +289,7 @@ def main():
         return
     hbm, how = _peaks()
     bytes_step = decode_bytes_per_step(dims, eng.S, A, 4 + NEW_TOKENS / 2)
+    traffic, traffic_src = ncu_traffic_bytes() if (A == 1 and PRESET == "large-v3") else (None, None)
     achieved = bytes_step / (step_ms * 1e-3) / 1e9
     tokens = A * NEW_TOKENS * world
     # log-mel (2) + conv stem (2) + 8 per encoder layer + final LayerNorm + cross K/V projections (2 per decoder layer)
@@ -297,7 +316,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": ("decode_mega_kernel (one persistent kernel per decoder step: 32 layers + LM head + greedy select)"
                                                  if mega else "decoder step (per-op gemv/attention/select kernels, one CUDA graph)"), "achieved": achieved,
-                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": how, "traffic": None,
+                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": how, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "bytes_per_step": bytes_step, "ms_per_decoder_step": step_ms},
     }
     if not args.no_cpu_baseline:
