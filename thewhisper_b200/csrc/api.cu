@@ -37,6 +37,7 @@ struct EncLayer {
 struct DecLayer {
   const float *ln1g, *ln1b, *bqkv, *bo, *ln2g, *ln2b, *xbq, *xbv, *xbo, *ln3g, *ln3b, *b1, *b2;
   const bf16 *wqkv, *wo, *xwq, *xwk, *xwv, *xwo, *w1, *w2;
+  const bf16 *wo_hm = nullptr, *xwo_hm = nullptr;  // optional head-major copies [H][D][64] of wo / xwo (decode_mega3)
 };
 
 struct GraphKey {
@@ -91,6 +92,8 @@ struct bw_engine {
   bool no_graph = false, simt = false, no_mega = false;
   int mega_flags = 0;  // BW_MEGA_FLAGS, re-read at every bw_decode_begin (each value has its own step graph)
   int mega_variant = 0;  // BW_MEGA_VARIANT: compile-time variant of decode_mega_kernel (decode_mega.cu V_* bits)
+  float* dx2 = nullptr;                    // decode_mega3: second residual-stream buffer
+  unsigned long long *acc_a = nullptr, *acc_b = nullptr;  // decode_mega3: fixed-point out-projection accumulators [D]
   unsigned long long* mega_ll = nullptr;  // self-validating activation words of the V_RELAXED variant
   size_t mega_ll_words = 0;
   int num_sms = 148;
@@ -257,8 +260,11 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
     m.ll = e->mega_ll;
     m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
     m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && !(m.flags & 32) && n_steps > 1) ? n_steps : 1;
+    m.dx2 = e->dx2; m.acc_a = e->acc_a; m.acc_b = e->acc_b;
+    for (size_t l = 0; l < e->dec.size(); ++l) { m.wo_hm[l] = e->dec[l].wo_hm; m.xwo_hm[l] = e->dec[l].xwo_hm; }
     int rc = -3;
-    if (m.flags & 32) rc = launch_decode_mega2(st, m, e->num_sms);
+    if ((m.flags & 128) && m.fuse_select) rc = launch_decode_mega3(st, m, e->num_sms);
+    if (rc == -3 && (m.flags & 32)) rc = launch_decode_mega2(st, m, e->num_sms);
     if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;
@@ -499,6 +505,12 @@ int bw_engine_finalize(bw_engine* e) {
     NEED(bf16, L.wo, p + "wo") NEED(float, L.bo, p + "bo") NEED(float, L.ln2g, p + "ln2.g") NEED(float, L.ln2b, p + "ln2.b")
     NEED(bf16, L.xwq, p + "xwq") NEED(float, L.xbq, p + "xbq") NEED(bf16, L.xwk, p + "xwk") NEED(bf16, L.xwv, p + "xwv")
     NEED(float, L.xbv, p + "xbv") NEED(bf16, L.xwo, p + "xwo") NEED(float, L.xbo, p + "xbo")
+    {
+      auto it = e->tensors.find(p + "wo_hm");
+      if (it != e->tensors.end()) L.wo_hm = static_cast<const bf16*>(it->second);
+      it = e->tensors.find(p + "xwo_hm");
+      if (it != e->tensors.end()) L.xwo_hm = static_cast<const bf16*>(it->second);
+    }
     NEED(float, L.ln3g, p + "ln3.g") NEED(float, L.ln3b, p + "ln3.b")
     NEED(bf16, L.w1, p + "w1") NEED(float, L.b1, p + "b1") NEED(bf16, L.w2, p + "w2") NEED(float, L.b2, p + "b2")
   }
@@ -527,6 +539,9 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
+  if (dalloc(e, "dx2", &e->dx2, (size_t)Qm * D)) return -1;
+  if (dalloc(e, "acc_a", &e->acc_a, (size_t)D + 8)) return -1;
+  if (dalloc(e, "acc_b", &e->acc_b, (size_t)D + 8)) return -1;
   e->mega_ll_words = (size_t)2 * ((size_t)D + c.ffn) + 64;
   if (dalloc(e, "mega_ll", &e->mega_ll, e->mega_ll_words)) return -1;
   if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] + per-CTA flags [32, 32 + SMs)
@@ -629,6 +644,8 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
   BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
   BW_CUDA_OK(cudaMemsetAsync(e->mega_ll, 0, sizeof(unsigned long long) * e->mega_ll_words, st));  // tags restart with the position
+  BW_CUDA_OK(cudaMemsetAsync(e->acc_a, 0, sizeof(unsigned long long) * e->D, st));
+  BW_CUDA_OK(cudaMemsetAsync(e->acc_b, 0, sizeof(unsigned long long) * e->D, st));
   iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope

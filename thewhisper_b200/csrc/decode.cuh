@@ -124,6 +124,12 @@ struct MegaArgs {
   int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
   int variant;       // compile-time kernel variant (decode_mega.cu V_* bits; BW_MEGA_VARIANT), 0 = default
   int n_steps;       // decoder steps in this launch (> 1 only with the V_MULTI variant and fused selection)
+  // decode_mega3.cu (attention fused with its out-projection): head-major copies [H][D][64] of the two out-projection
+  // matrices per layer, the second residual-stream buffer and the two 64-bit fixed-point accumulators [D] (zero between steps)
+  const bf16* wo_hm[MEGA_MAXL];
+  const bf16* xwo_hm[MEGA_MAXL];
+  float* dx2;
+  unsigned long long *acc_a, *acc_b;
   unsigned long long* ll;  // V_RELAXED: [2 * (D + ffn)] {tag, value} words: dx at 0, dh at ll_off_dh; zeroed by bw_decode_begin
   int ll_off_dh;
 };
@@ -133,6 +139,9 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
 // second generation (decode_mega2.cu): K-parallel GEMV phases with x in registers, one sequence; MegaArgs::flags bit 5
 // (BW_MEGA_FLAGS=32) selects it; -3 -> the caller falls back to launch_decode_mega
 int launch_decode_mega2(cudaStream_t st, const MegaArgs& a, int num_sms);
+// third generation (decode_mega3.cu): attention phases fused with their out-projections, 4 grid barriers per layer;
+// MegaArgs::flags bit 7 (BW_MEGA_FLAGS=128, + 64 is irrelevant there) selects it; -3 -> fall back
+int launch_decode_mega3(cudaStream_t st, const MegaArgs& a, int num_sms);
 
 int launch_gemv(cudaStream_t st, const GemvArgs& a);
 int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax);

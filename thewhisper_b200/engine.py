@@ -121,6 +121,10 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, enc_pos: torch.Te
         out[o + "xwv"] = mat(sd[p + "encoder_attn.v_proj.weight"])
         out[o + "xbv"] = vec(sd[p + "encoder_attn.v_proj.bias"])
         out[o + "xwo"] = mat(sd[p + "encoder_attn.out_proj.weight"])
+        # head-major copies [H][D][64] of the two out-projections: the slab of a fused (head, row slice) item of the
+        # third-generation decoder-step kernel (csrc/decode_mega3.cu) is contiguous in them
+        out[o + "wo_hm"] = mat(sd[p + "self_attn.out_proj.weight"].reshape(D, dims.n_heads, 64).permute(1, 0, 2))
+        out[o + "xwo_hm"] = mat(sd[p + "encoder_attn.out_proj.weight"].reshape(D, dims.n_heads, 64).permute(1, 0, 2))
         out[o + "xbo"] = vec(sd[p + "encoder_attn.out_proj.bias"])
         out[o + "ln3.g"] = vec(sd[p + "final_layer_norm.weight"])
         out[o + "ln3.b"] = vec(sd[p + "final_layer_norm.bias"])
