@@ -21,62 +21,17 @@
 // decode_mega.cu's.  Slab phases keep their parity (even phases in region 0, odd ones at the pool's start); the slab of
 // the phase that follows an attention phase can only be requested when the attention scratch (which overlays region 0)
 // is free again, i.e. just before the grid barrier, which hides the copy.
-#include <math.h>
-
-#include "decode.cuh"
-#include "kernels.h"
+#include "decode_mega_common.cuh"
 
 namespace bw {
 
 namespace {
 
-constexpr int MT = 384;        // threads per CTA
-constexpr int MW = MT / 32;    // warps per CTA
-constexpr int DMA_T = MT - 32;  // first lane of the last warp: issues every TMA operation
-constexpr int KG = MT / 8;     // key groups of 8 lanes in the attention phases
-constexpr int MAXKEYS = 448;   // self-attention keys held in smem (Tmax)
-constexpr int XKMAX = 256;     // cross-attention keys per work item held in smem
-constexpr int MAXD = 1280;
-constexpr int ATT_OFF = 32 * 1024;  // attention scratch starts here inside the pool (above the small region-1 slabs)
+using namespace mega;
+
 constexpr int RSMAX = MW * 16;  // out-projection rows of one (head, slice) item: 16 per warp
 constexpr float FIX_SCALE = 16777216.f;  // 2^24
 constexpr int CNT_QKV = 256, CNT_XQ = 288, CNT_XHEAD = 384;  // word offsets of the per-head counters inside MegaArgs::bar
-
-__device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
-  float2 t;
-  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
-}
-__device__ __forceinline__ void cp_async16m(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_allm() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// TMA bulk copy global -> this CTA's smem, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned atom_acq_rel_add(unsigned* p, unsigned v) {
-  unsigned old;
-  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ long long global_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 
 
 __device__ __forceinline__ unsigned long long f2fix(float v) { return (unsigned long long)__float2ll_rn(v * FIX_SCALE); }
@@ -249,28 +204,10 @@ struct Pre {
   float4 g, b;  // gamma / beta of elements [4*tid, 4*tid + 4)
 };
 
-__device__ __forceinline__ void issue_rows(uint8_t* slab, uint64_t* bar, const bf16* W, int K, int R, int n, int N, int lane) {
-  if (lane == 0) {
-    const uint32_t row_bytes = (uint32_t)K * 2;
-    mbar_arrive_expect_tx(bar, row_bytes * R);
-    for (int r = 0; r < R; ++r) {
-      const int row = min(n + r, N - 1);
-      bulk_g2s(slab + (size_t)r * row_bytes, W + (long long)row * K, row_bytes, bar);
-    }
-  }
-}
-
-// DRAM -> L2 only (no smem, no completion): the rows a warp will pull into its slab one phase later
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// The rows of a CTA's 12 warps are contiguous in memory (rows [blockIdx*12*R, +12*R)) and so are their slabs in smem: one
-// TMA operation per CTA and phase.  (Per-row operations cost ~10 ns of TMA issue each -- 36 of them per SM and phase were
-// 0.35 us on the critical path.)
+// The rows of a CTA are contiguous in memory and so are their slabs in smem: one TMA operation per CTA and phase.
 __device__ __forceinline__ void l2_prefetch_phase(const GemvDesc& d) {
   if (threadIdx.x == DMA_T && !d.lm && d.n0 < d.nend) l2_prefetch(d.W + (long long)d.n0 * d.K, (uint32_t)(d.nend - d.n0) * d.K * 2);
 }
-
 __device__ __forceinline__ void l2_prefetch_slice(const SliceDesc& s) {
   if (threadIdx.x == DMA_T && s.rows > 0) l2_prefetch(s.W, (uint32_t)s.rows * 128u);
 }
@@ -396,52 +333,6 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   stage_done_stagers();
 }
 
-template <int MB, int R>
-__device__ __forceinline__ void dot_chunk(const uint8_t* slab, const float* xs, int K, int k0, bool hi, float (&s)[R][MB]) {
-  float4 x0[MB], x1[MB];
-#pragma unroll
-  for (int m = 0; m < MB; ++m) {
-    x0[m] = *reinterpret_cast<const float4*>(&xs[m * K + k0]);
-    x1[m] = hi ? *reinterpret_cast<const float4*>(&xs[m * K + k0 + 128]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const uint2 wa = *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0) * 2);
-    const uint2 wc = hi ? *reinterpret_cast<const uint2*>(slab + ((size_t)r * K + k0 + 128) * 2) : make_uint2(0u, 0u);
-    const float2 a0 = unpack_bf16(wa.x), a1 = unpack_bf16(wa.y), c0 = unpack_bf16(wc.x), c1 = unpack_bf16(wc.y);
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      float t = s[r][m], u = 0.f;
-      t = fmaf(a0.x, x0[m].x, t); u = fmaf(c0.x, x1[m].x, u);
-      t = fmaf(a0.y, x0[m].y, t); u = fmaf(c0.y, x1[m].y, u);
-      t = fmaf(a1.x, x0[m].z, t); u = fmaf(c1.x, x1[m].z, u);
-      t = fmaf(a1.y, x0[m].w, t); u = fmaf(c1.y, x1[m].w, u);
-      s[r][m] = t + u;
-    }
-  }
-}
-
-// The full 256-element chunks run branch-free (unrolled by 5 so the loads of several chunks are in flight together: with a
-// guard per chunk the compiler serialised load -> convert -> FMA chunk by chunk, ~120 cycles each); a ragged tail
-// (K % 256 != 0: only the small test models) takes the guarded path.
-template <int MB, int R>
-__device__ __forceinline__ void dot_rows(const uint8_t* slab, const float* xs, int K, float (&acc)[3][MB], int lane) {
-  float s[R][MB];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int m = 0; m < MB; ++m) s[r][m] = 0.f;
-  const int nfull = K >> 8;
-  int k0 = lane * 4;
-#pragma unroll 5
-  for (int c = 0; c < nfull; ++c, k0 += 256) dot_chunk<MB, R>(slab, xs, K, k0, true, s);
-  if (k0 < K) dot_chunk<MB, R>(slab, xs, K, k0, (k0 + 128) < K, s);
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int m = 0; m < MB; ++m) acc[r][m] = (r < R) ? warp_sum(s[r < R ? r : 0][m]) : 0.f;
-}
-
 // lanes 8r finish row n + r  (R <= 3, one sequence)
 __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc)[3][1], float bias, int n, float res, int D, int Tmax, int pos, int lane) {
   const int m = lane & 7, r_sel = lane >> 3;
@@ -461,31 +352,6 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
   }
 }
 
-// Warp totals of NV = 16 per-lane partial sums by a transposing butterfly (decode_mega2.cu): afterwards every lane holds the
-// total of row (lane >> 1).
-__device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
-  int n = 16;
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    if (n > 1) {
-      const int h = n >> 1;
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < h) {
-          const float keep = up ? v[j + h] : v[j];
-          const float send = up ? v[j] : v[j + h];
-          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-        }
-      }
-      n = h;
-    } else {
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
-    }
-  }
-  return v[0];
-}
-
 // Out-projection slice of a fused attention item: rows [0, s.rows) of the [rows][64] bf16 slab against the head's 64
 // attention outputs (a_s, smem); warp w owns rows 16w .. 16w + 15, lane l columns 2l, 2l + 1; the totals are ADDED to the
 // 64-bit fixed-point accumulator acc[s.r0 + row] (integer adds commute: the result does not depend on the order of the heads).
@@ -502,114 +368,9 @@ __device__ __forceinline__ void outproj_slice(const uint8_t* slab, const float* 
     }
     v[i] = t;
   }
-  const float tot = treduce16(v, lane);
+  const float tot = treduce<16>(v, lane);
   const int row = warp * 16 + (lane >> 1);
   if ((lane & 1) == 0 && row < s.rows) atomicAdd(acc + s.r0 + row, f2fix(tot));
-}
-
-// Scores, softmax numerators and the un-normalised P.V of one work item whose n <= NJ*KG keys sit in smem (rows of 128 B).
-// Key group g (8 lanes, 8 dims each) owns keys g, g + KG, ...: its scores stay in registers, all smem reads of a pass are
-// issued together (fully unrolled, predicated), and there are two CTA barriers in all: one for the maximum, one for the
-// final fold of (sum, 64 outputs) across warps.  Returns max / sum / (threads < 64) the output sums.
-// red: [2][MW] floats, redo: [MW][64 + 8] floats.
-template <int NJ>
-__device__ __forceinline__ void attend_smem(const uint8_t* sK, const uint8_t* sV, float* redo, float* red, const float (&qv)[8], int n,
-                                            float* score_out, float& mx_out, float& sum_out, float& ov_out) {
-  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // separate passes so that the NJ independent chains overlap: loads + FMAs of all keys, then the three shuffle stages
-  // across all keys (one dependent shuffle chain per key cost ~150 cycles per key when interleaved with the FMAs)
-  float d[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int kk = grp + j * KG;
-    float t0 = 0.f, t1 = 0.f;
-    if (kk < n) {
-      float kf[8];
-      unpack8m(*reinterpret_cast<const uint4*>(sK + kk * 128 + sub * 16), kf);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        t0 = fmaf(qv[i], kf[i], t0);
-        t1 = fmaf(qv[i + 4], kf[i + 4], t1);
-      }
-    }
-    d[j] = t0 + t1;
-  }
-#pragma unroll
-  for (int st = 1; st < 8; st <<= 1) {
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], st);
-  }
-  float lmax = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int kk = grp + j * KG;
-    if (kk < n) {
-      lmax = fmaxf(lmax, d[j]);
-      if (score_out && sub == 0) score_out[kk] = d[j];
-    }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) red[warp] = lmax;
-  __syncthreads();
-  float mx = red[0];
-#pragma unroll
-  for (int w = 1; w < MW; ++w) mx = fmaxf(mx, red[w]);
-  float acc[8], lsum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  {  // one exp per key (not one per lane): lane (j & 7) of the group exponentiates key j, the group shares it by shuffle
-    float mine = 0.f, mine2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j)
-      if ((j & 7) == sub) {
-        if (j < 8) mine = d[j];
-        else mine2 = d[j];
-      }
-    mine = __expf(mine - mx);
-    if (NJ > 8) mine2 = __expf(mine2 - mx);
-    const int gl = lane & 24;  // first lane of this group of 8
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const float e = __shfl_sync(0xffffffffu, j < 8 ? mine : mine2, gl + (j & 7));
-      d[j] = (grp + j * KG < n) ? e : 0.f;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int kk = grp + j * KG;
-    if (kk < n) {
-      lsum += d[j];
-      float vf[8];
-      unpack8m(*reinterpret_cast<const uint4*>(sV + kk * 128 + sub * 16), vf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(d[j], vf[i], acc[i]);
-    }
-  }
-  // fold the 4 key groups of a warp with shuffles (lanes with equal sub), then the 12 warp partials through smem
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-  }
-  lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);  // (all 8 lanes of a group hold the same sum)
-  lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
-  if (lane < 8) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) redo[warp * 72 + lane * 8 + i] = acc[i];
-    if (lane == 0) redo[warp * 72 + 64] = lsum;
-  }
-  __syncthreads();
-  float ov = 0.f, ls = 0.f;
-#pragma unroll
-  for (int w = 0; w < MW; ++w) ls += redo[w * 72 + 64];
-  if (threadIdx.x < 64) {
-#pragma unroll
-    for (int w = 0; w < MW; ++w) ov += redo[w * 72 + threadIdx.x];
-  }
-  mx_out = mx;
-  sum_out = ls;
-  ov_out = ov;
 }
 
 // smem carve-up (dynamic): red [64] | xs [ffn] | pool: weight slabs from 0, attention scratch from ATT_OFF
@@ -957,35 +718,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
       }
     }
   }
-}
-
-// smem plan: returns the dynamic smem bytes and the offset of slab region 0 (0: single-buffered, everything at the pool's start)
-size_t mega_smem_plan(int mb, int D, int ffn, int num_sms, bool want_dbuf, int* p0_off) {
-  // rows of a CTA, rounded up to whole active warps: the unused rows of the last active warp are still read (and discarded)
-  auto rc = [&](int n) {
-    const int rows = (n + num_sms - 1) / num_sms, R = (rows + MW - 1) / MW;
-    return (size_t)((rows + R - 1) / R * R);
-  };
-  const size_t attn = (size_t)MAXKEYS * 256 + (size_t)(MW * 72) * sizeof(float);
-  const size_t xattn = (size_t)2 * XKMAX * 128 + (size_t)(MW * 72) * sizeof(float);
-  const size_t att = ATT_OFF + (attn > xattn ? attn : xattn);
-  const size_t lm = (size_t)MW * 2 * 2 * D * 2;  // LM head: 2 stages of row pairs per warp
-  size_t r1 = rc(D) * ffn * 2;                   // region 1: out-proj / cross out-proj (K = D), fc2 (K = ffn)
-  if (rc(D) * D * 2 > r1) r1 = rc(D) * D * 2;
-  size_t r0 = rc(3 * D) * D * 2;                 // region 0: QKV, cross-q, fc1
-  if (rc(ffn) * D * 2 > r0) r0 = rc(ffn) * D * 2;
-  if (rc(D) * D * 2 > r0) r0 = rc(D) * D * 2;
-  const size_t fixed = 64 * sizeof(float) + (size_t)mb * ffn * sizeof(float) + 128;
-  const size_t limit = 227 * 1024 - 8 * 1024;   // the opt-in limit includes the static smem (layer table, barriers)
-  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
-  const size_t off = (r1 + 127) / 128 * 128;
-  const size_t pool_d = mx(mx(off + r0, att), lm);
-  if (want_dbuf && fixed + pool_d <= limit) {
-    *p0_off = (int)off;
-    return fixed + pool_d;
-  }
-  *p0_off = 0;
-  return fixed + mx(mx(mx(r0, r1), att), lm);
 }
 
 }  // namespace
