@@ -259,12 +259,11 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
     m.variant = e->mega_variant;
     m.ll = e->mega_ll;
     m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
-    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && !(m.flags & (32 | 128)) && n_steps > 1) ? n_steps : 1;
+    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && !(m.flags & 128) && n_steps > 1) ? n_steps : 1;
     m.dx2 = e->dx2; m.acc_a = e->acc_a; m.acc_b = e->acc_b;
     for (size_t l = 0; l < e->dec.size(); ++l) { m.wo_hm[l] = e->dec[l].wo_hm; m.xwo_hm[l] = e->dec[l].xwo_hm; }
     int rc = -3;
     if ((m.flags & 128) && m.fuse_select) rc = launch_decode_mega3(st, m, e->num_sms);
-    if (rc == -3 && (m.flags & 32)) rc = launch_decode_mega2(st, m, e->num_sms);
     if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;

@@ -109,7 +109,7 @@ struct MegaArgs {
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
   int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments);
-                     // bit5 (32): decode_mega2.cu (K-parallel GEMV phases); bit6 (64): the staging warps do not wait for the DMA warp
+                     // bit6 (64): the staging warps do not wait for the DMA warp; bit7 (128): decode_mega3.cu
   // greedy token selection fused behind the LM head (no timestamp rules, one beam): masked arg-max by 64-bit atomicMax,
   // the last CTA to finish writes the token, handles EOS / pad and advances the position -- no select kernel
   int fuse_select;
@@ -136,11 +136,9 @@ struct MegaArgs {
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
-// second generation (decode_mega2.cu): K-parallel GEMV phases with x in registers, one sequence; MegaArgs::flags bit 5
-// (BW_MEGA_FLAGS=32) selects it; -3 -> the caller falls back to launch_decode_mega
-int launch_decode_mega2(cudaStream_t st, const MegaArgs& a, int num_sms);
-// third generation (decode_mega3.cu): attention phases fused with their out-projections, 4 grid barriers per layer;
-// MegaArgs::flags bit 7 (BW_MEGA_FLAGS=128, + 64 is irrelevant there) selects it; -3 -> fall back
+// decode_mega3.cu: attention phases fused with their out-projections, 4 grid barriers per layer; MegaArgs::flags bit 7
+// (BW_MEGA_FLAGS=128) selects it; -3 -> the caller falls back to launch_decode_mega.  (A K-parallel generation,
+// decode_mega2.cu, was measured 3.8 % slower and removed after commit c66a715: profiles/r1_v8_summary.md.)
 int launch_decode_mega3(cudaStream_t st, const MegaArgs& a, int num_sms);
 
 int launch_gemv(cudaStream_t st, const GemvArgs& a);

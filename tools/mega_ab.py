@@ -15,7 +15,7 @@ from tools.profile_decode import random_state_dict  # noqa: E402
 
 
 def main():
-    variants = [v for v in os.environ.get("BW_AB", "64:0,64:1,64:3,64:5,64:9,64:7,64:15,32:0").split(",") if v]
+    variants = [v for v in os.environ.get("BW_AB", "64:0,64:1,64:3,64:5,64:9,64:7,64:15,192:0").split(",") if v]
     A = int(os.environ.get("BW_A", "1"))
     dev = torch.device("cuda:0")
     dims = ModelDims.from_hf_config(S.make_hf_config(os.environ.get("BW_PRESET", "large-v3")))
