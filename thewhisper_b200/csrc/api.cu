@@ -259,7 +259,7 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
     m.variant = e->mega_variant;
     m.ll = e->mega_ll;
     m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
-    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && !(m.flags & 128) && n_steps > 1) ? n_steps : 1;
+    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && n_steps > 1) ? n_steps : 1;
     m.dx2 = e->dx2; m.acc_a = e->acc_a; m.acc_b = e->acc_b;
     for (size_t l = 0; l < e->dec.size(); ++l) { m.wo_hm[l] = e->dec[l].wo_hm; m.xwo_hm[l] = e->dec[l].xwo_hm; }
     int rc = -3;

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * MW + warp, GW = gridDim.x * MW;
   const int D = a.D, H = a.H;
-  const int pos = *a.pos;
+  const int pos0 = *a.pos;
   GridBar bar{a.bar, gridDim.x, 0u};
   const int nsplit = a.nsplit;  // row slices of the self-attention items = key splits of the cross-attention items
   const int ks = (a.S + nsplit - 1) / nsplit;
@@ -417,6 +417,13 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
   }
   __syncthreads();
 
+  // MegaArgs::n_steps decoder steps per launch: the previous step's last CTA wrote the token and advanced the position
+  // before it arrived at the barrier that ends a step, so both are read from L2; the per-head counters count layers across
+  // the steps of a launch
+  const int nsteps = a.n_steps > 1 ? a.n_steps : 1;
+  for (int step = 0; step < nsteps; ++step) {
+  const int pos = step > 0 ? __ldcg(a.pos) : pos0;
+  const int lbase = step * a.L;
   // ---- embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   GemvDesc cur = make_desc(a, sl, 0, 0);
   Pre pre;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
   prefetch_phase(cur, pre, pool, &wbar[warp], gw, warp, lane);
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < D; i += MT) {
-      const int tok = a.tokens[pos];
+      const int tok = step > 0 ? __ldcg(a.tokens + pos) : a.tokens[pos];
       a.dx[i] = __bfloat162float(a.embed[(long long)tok * D + i]) + a.dec_pos[(long long)pos * D + i];
     }
   }
@@ -522,7 +529,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
             cp_async16m(sK + s * 128 + sub * 16, L.self_k + off);
             cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
           }
-          counter_wait(a.bar + CNT_QKV + ih, (unsigned)(l + 1) * head_expected(ih, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
+          counter_wait(a.bar + CNT_QKV + ih, (unsigned)(lbase + l + 1) * head_expected(ih, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
           const int n = pos + 1;
           for (int s = pos + grp; s < n; s += KG) {
             const long long off = (long long)s * D + ih * 64 + sub * 8;
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
               bulk_g2s(sV, L.cross_v + ((long long)ih * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
             }
           }
-          counter_wait(a.bar + CNT_XQ + ih, (unsigned)(l + 1) * head_expected(ih, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
+          counter_wait(a.bar + CNT_XQ + ih, (unsigned)(lbase + l + 1) * head_expected(ih, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
           float qv[8];
           {
             const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dq + ih * 64 + sub * 8));
@@ -591,7 +598,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
           __syncthreads();
           // exchange among the nsplit CTAs of this head: everybody arrives, everybody waits, everybody merges
           if (threadIdx.x == MT - 1) red_release_add(a.bar + CNT_XHEAD + ih, 1u);
-          counter_wait(a.bar + CNT_XHEAD + ih, (unsigned)(l + 1) * (unsigned)nsplit);
+          counter_wait(a.bar + CNT_XHEAD + ih, (unsigned)(lbase + l + 1) * (unsigned)nsplit);
           if (threadIdx.x < 64) {
             const long long hb = (long long)ih * nsplit;
             float pm[XSPLIT], pl[XSPLIT], po[XSPLIT];
@@ -718,6 +725,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
       }
     }
   }
+  if (step + 1 < nsteps) bar.sync();  // the token and the position of the next step are in global memory
+  }  // step
 }
 
 }  // namespace
@@ -726,6 +735,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega3_kernel(const __grid_consta
 // supports (more than one sequence, no head-major out-projection copies bound, no fused greedy selection needed is fine).
 int launch_decode_mega3(cudaStream_t st, const MegaArgs& a, int num_sms) {
   if (a.Q != 1 || a.trace || !a.dx2 || !a.acc_a || !a.acc_b) return -3;
+  if (a.n_steps > 1 && !a.fuse_select) return -3;
   for (int l = 0; l < a.L; ++l)
     if (!a.wo_hm[l] || !a.xwo_hm[l]) return -3;
   if (a.L > MEGA_MAXL || a.D > MAXD || a.ffn > 5120 || a.D % 8 != 0 || a.ffn % 8 != 0 || a.Tmax > MAXKEYS || a.H > 32) return -3;

@@ -13,4 +13,4 @@ for v in 3 5 17 23 33 55 15; do
 done
 echo "== decode_mega3 (BW_MEGA_FLAGS=192: attention fused with its out-projection, 4 grid barriers per layer)"
 BW_MEGA_FLAGS=192 timeout 600 python -m pytest tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -k "teacher_forced or batch_rows" 2>&1 | grep -v Warning | tail -6 | tee gpurun_out/variants_tests_mega3.log
-BW_AB="64:0,192:0,64:0,192:0" timeout 300 python tools/mega_ab.py 2>&1 | tail -5 | tee gpurun_out/variants_ab_mega3.log
+BW_AB="64:0,192:0,192:33,64:0,192:0,192:33" timeout 300 python tools/mega_ab.py 2>&1 | tail -7 | tee gpurun_out/variants_ab_mega3.log
