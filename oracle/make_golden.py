@@ -272,10 +272,12 @@ def main():
         golden_model(ASRPipeline, "tiny-test", "tiny10", chunk_s=10, audio_s=25.0, gain=8.0)
         golden_model(ASRPipeline, "small-test", "small30", chunk_s=30, audio_s=70.0, gain=8.0)
     if a.large:
+        # the BASELINE.json configs C1 / C2 at their real dimensions.  layer_gain 4: with the plain HF init these sizes collapse to
+        # one repeated token whatever the audio (gain 1 -> 29511 x 16); gain 4 gives varied, audio-dependent sequences
         golden_model(ASRPipeline, "large-v3-turbo", "turbo10", chunk_s=10, audio_s=10.0, n_tf=12, max_new=16,
-                     do_pipeline=False)
+                     do_pipeline=False, gain=4.0)
         golden_model(ASRPipeline, "large-v3", "large30", chunk_s=30, audio_s=30.0, n_tf=12, max_new=32,
-                     do_pipeline=False)
+                     do_pipeline=False, gain=4.0)
 
 
 if __name__ == "__main__":

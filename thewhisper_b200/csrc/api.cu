@@ -40,10 +40,13 @@ struct DecLayer {
   const bf16 *wo_hm = nullptr, *xwo_hm = nullptr;  // optional head-major copies [H][D][64] of wo / xwo (decode_mega3)
 };
 
+// Everything a captured step graph bakes in as kernel parameters: a decode that differs in any of these gets its own graph
+// (round-1 advisor: eos / pad / timestamp ids were missing, a second decode with other ids replayed the old ones).
 struct GraphKey {
-  int A, G, begin_index, ts_rules, align, variant;
+  int A, G, begin_index, ts_rules, align, variant, eos, pad, ts_begin, no_ts;
   bool operator<(const GraphKey& o) const {
-    return std::tie(A, G, begin_index, ts_rules, align, variant) < std::tie(o.A, o.G, o.begin_index, o.ts_rules, o.align, o.variant);
+    return std::tie(A, G, begin_index, ts_rules, align, variant, eos, pad, ts_begin, no_ts) <
+           std::tie(o.A, o.G, o.begin_index, o.ts_rules, o.align, o.variant, o.eos, o.pad, o.ts_begin, o.no_ts);
   }
 };
 
@@ -659,17 +662,25 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   }
   if (!e->no_graph) {
     GraphKey key{A, G, opts->begin_index, opts->timestamp_rules * 4 + (opts->max_initial_timestamp_index + 1) * 8, opts->record_alignment,
-                 e->mega_flags * 4 + e->mega_variant * 65536 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0)};
+                 e->mega_flags * 4 + e->mega_variant * 65536 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0),
+                 opts->eos_token, opts->pad_token, opts->timestamp_begin, opts->no_timestamps_token};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
       cudaStream_t cs;
       BW_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
-      BW_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      const int rc = step_impl(e, cs);
-      const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-      if (rc != 0 || ce != cudaSuccess) {
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        BW_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = step_impl(e, cs);
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc == 0 && ce == cudaSuccess) break;
         if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        cudaGetLastError();
+        if (attempt == 0 && g_mega_coop == 1) {  // a driver that cannot capture a cooperative launch: plain launch, as in round 1
+          g_mega_coop = 0;
+          continue;
+        }
         cudaStreamDestroy(cs);
         if (rc == 0) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
         return -1;

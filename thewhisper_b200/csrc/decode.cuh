@@ -136,6 +136,7 @@ struct MegaArgs {
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
+extern int g_mega_coop;  // 1: the persistent step kernels are launched cooperatively (co-residency guaranteed by the driver)
 // decode_mega3.cu: attention phases fused with their out-projections, 4 grid barriers per layer; MegaArgs::flags bit 7
 // (BW_MEGA_FLAGS=128) selects it; -3 -> the caller falls back to launch_decode_mega.  (A K-parallel generation,
 // decode_mega2.cu, was measured 3.8 % slower and removed after commit c66a715: profiles/r1_v8_summary.md.)

@@ -1,7 +1,7 @@
 // One persistent kernel per decoder step (q_len = 1, one beam per audio, up to 2 sequences).
 //
 // Why: with one kernel per op the step is 259 launches and every op pays its own chain of dependent global round
-// trips; a step that should take 0.32 ms (2.07 GB at the measured 6.5 TB/s) took 1.7 ms
+// trips; a step that should take 0.28 ms (1.86 GB at the measured 6.5 TB/s) took 1.7 ms
 // (profiles/r1_v1_launches_summary.md).  Here the whole step -- embedding, 32 x (LN1+QKV, self-attention, out-proj,
 // LN2+cross-q, cross-attention, out-proj, LN3+fc1+GELU, fc2), final LN + tied LM head -- runs in ONE kernel of one CTA
 // per SM, phases separated by a grid barrier.
@@ -872,6 +872,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
 
 }  // namespace
 
+int g_mega_coop = -1;  // -1: read BW_MEGA_COOP on first use; the engine clears it if a cooperative launch cannot be captured
+
 // Launches the persistent step kernel on `st`.  Returns -3 when the configuration is outside what it supports
 // (the caller then uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
@@ -897,14 +899,31 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
   // MegaArgs::variant picks a compile-time variant (see V_* at the top); two sequences always run the default
+  // Co-residency of the 148 CTAs (round-1 advisor): the grid barriers spin, so a CTA that is not scheduled deadlocks the rest until
+  // the 2^32-cycle timeout traps.  (1) the occupancy calculator must promise one CTA per SM, else -3 (per-op path); (2) the launch is
+  // cooperative, so the driver either runs the whole grid at once or fails the launch (another kernel holding SMs: an error code at
+  // the C-ABI, not a poisoned context).  BW_MEGA_COOP=0 falls back to the plain launch of round 1.
+  int& coop = g_mega_coop;
+  if (coop < 0) {
+    const char* ev = getenv("BW_MEGA_COOP");
+    coop = (ev && ev[0] == '0') ? 0 : 1;
+  }
 #define BW_MEGA_LAUNCH(MB, VAR)                                                                                            \
   {                                                                                                                        \
     static size_t attr = 0;                                                                                                \
     if (smem > attr) {                                                                                                     \
       BW_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<MB, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      int per_sm = 0;                                                                                                      \
+      BW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel<MB, VAR>, MT, smem));           \
+      if (per_sm < 1) return -3;                                                                                           \
       attr = smem;                                                                                                         \
     }                                                                                                                      \
-    decode_mega_kernel<MB, VAR><<<num_sms, MT, smem, st>>>(b);                                                             \
+    cudaLaunchConfig_t cfg{};                                                                                              \
+    cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(MT); cfg.dynamicSmemBytes = smem; cfg.stream = st;                    \
+    cudaLaunchAttribute at[1];                                                                                             \
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;                                                  \
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;                                                                           \
+    BW_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<MB, VAR>, b));                                                  \
   }
   if (mb == 2) {
     BW_MEGA_LAUNCH(2, 0u)

@@ -761,7 +761,18 @@ int launch_decode_mega3(cudaStream_t st, const MegaArgs& a, int num_sms) {
     BW_CUDA_OK(cudaFuncSetAttribute(decode_mega3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  decode_mega3_kernel<<<num_sms, MT, smem, st>>>(b);
+  {  // cooperative launch: the whole grid is co-resident or the launch fails (see launch_decode_mega)
+    if (g_mega_coop < 0) {
+      const char* ev = getenv("BW_MEGA_COOP");
+      g_mega_coop = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(MT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = g_mega_coop ? 1 : 0;
+    BW_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega3_kernel, b));
+  }
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }
