@@ -60,6 +60,10 @@ typedef struct bw_decode_opts {
 const char* bw_last_error(void);
 int bw_abi_version(void);
 int bw_device_count(void);
+/* bit 0: the persistent decoder-step kernel is launched cooperatively; bit 1: the batched step uses programmatic dependent
+ * launch.  Both are on by default and are cleared (once, process-wide) if the driver cannot capture such a launch in a graph;
+ * valid after the first bw_decode_begin. */
+int bw_runtime_flags(void);
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
 int bw_engine_create(const bw_config* cfg, bw_engine** out);
@@ -107,6 +111,10 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
  * frames (<= S); out_host [n_tokens + 1] seconds */
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision,
                        float* out_host, void* stream);
+/* the same for n audios in one pass (4 kernel launches + one D2H whatever n is): audio[i], n_tokens[i], num_frames[i];
+ * out_host [n][out_pitch] floats, out_pitch >= max n_tokens + 1 */
+int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
+                             float time_precision, float* out_host, int32_t out_pitch, void* stream);
 
 /* ---- host-side post-processing (no CUDA) ---------------------------------------------------------------------- */
 /* Seam merge of overlapping chunks: the reference's patched `_find_longest_common_sequence`
@@ -117,9 +125,17 @@ int bw_host_merge_overlapping(const int32_t* tokens, const int32_t* lens, int32_
                               int32_t* out_tokens, double* out_ts, int32_t* out_len);
 
 /* ---- single-op entry points (used by the parity tests; same kernels as the engine) --------------------------- */
-/* C[M,N] = epi(A[M,K] W[N,K]^T): impl 0 = tcgen05, 1 = CUDA-core comparator.  out_is_f32 selects the output type. */
+/* C[M,N] = epi(A[M,K] W[N,K]^T): impl 0 = tcgen05, 1 = CUDA-core comparator, 2 = tcgen05 CTA pairs (cta_group::2, persistent).  out_is_f32 selects the output type. */
 int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,
                const float* residual, void* out, int32_t out_is_f32, int32_t impl, int32_t force_bn, void* stream);
+/* The two building blocks of the batched (tensor-core) decoder step.  Split-K GEMM: split z of `ksplit` writes the raw fp32 partial
+ * sums of its k range at out_partials + z * M * N ([ksplit_used][M][N]; *ksplit_used <= ksplit); W has n_valid (<= N) rows in
+ * memory, rows beyond read as zero (tied LM head).  force_bn: 0 auto, 32 (decoder tile), 64, 128, 256. */
+int bw_op_gemm_splitk(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t n_valid, int32_t ksplit, int32_t force_bn,
+                      float* out_partials, int32_t* ksplit_used, void* stream);
+/* x[q] += bias + sum_s partials[s][q] (s ascending: deterministic), y[q] = LayerNorm(x[q]) as bf16 (y may be NULL). */
+int bw_op_resid_ln(float* x, const float* partials, int32_t nsplit, const float* bias, const float* ln_g, const float* ln_b, void* y_bf16,
+                   int32_t Q, int32_t D, void* stream);
 /* qkv [B*S, 3D] bf16 -> out [B*S, D] bf16; vt_scratch [B, H, 64, Spad] bf16 (Spad = S rounded up to 8) */
 int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int32_t S, int32_t H, int32_t impl, void* stream);
 int bw_op_layernorm(const float* x, const float* g, const float* b, void* out, int32_t out_is_f32, int32_t rows, int32_t D,

@@ -148,6 +148,12 @@ class StubEngine:
             gen.append(row[: cut[0]] if len(cut) else row)
         return gen, toks, done
 
+    def word_timestamps_batch(self, audios, n_tokens, num_frames, time_precision: float = 0.02) -> np.ndarray:
+        out = np.zeros((len(audios), int(max(n_tokens)) + 1), dtype=np.float32)
+        for i, (a, t, f) in enumerate(zip(audios, n_tokens, num_frames)):
+            out[i, : t + 1] = self.word_timestamps(a, t, f, time_precision)
+        return out
+
     def word_timestamps(self, audio: int, n_tokens: int, num_frames: int, time_precision: float = 0.02) -> np.ndarray:
         w = self._align[audio][:, :n_tokens]
         return whisper_ref.token_timestamps(w, num_frames, time_precision)

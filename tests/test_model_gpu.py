@@ -128,15 +128,17 @@ def test_encoder_parity(cuda, tag, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("tag", ["tiny10", "small30"])
-@pytest.mark.parametrize("path", ["mega", "perop"])
+@pytest.mark.parametrize("path", ["mega", "perop", "batched"])
 def test_teacher_forced_logits_and_greedy(cuda, tag, path, monkeypatch):
-    """path: the persistent one-kernel decoder step (default) or the per-op kernels (BW_NO_MEGA=1; also what beams and
-    batches > 8 use)."""
+    """path: the persistent one-kernel decoder step (default), the per-op GEMV kernels (BW_NO_MEGA=1; beams / timestamp rules
+    on one or two sequences) or the batched tensor-core step (what >= 3 sequences run; forced here for one sequence)."""
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
 
-    if path == "perop":
+    if path != "mega":
         monkeypatch.setenv("BW_NO_MEGA", "1")
+    if path == "batched":
+        monkeypatch.setenv("BW_BATCH_MIN", "1")
     meta, gold, model = _model_case(tag)
     chunk = meta["chunk_s"]
     eng = _engine(model, chunk, max_audios=1)
@@ -188,14 +190,21 @@ def test_teacher_forced_logits_and_greedy(cuda, tag, path, monkeypatch):
         assert gen.tolist() == g[: len(gen)].tolist()
 
 
-@pytest.mark.parametrize("path", ["mega", "perop"])
+@pytest.mark.parametrize("path", ["mega", "perop", "batched"])
 def test_batch_rows_agree(cuda, path, monkeypatch):
-    """B=3 audios decoded together give the tokens of the B=1 runs (batched gemv/cross-attention paths)."""
+    """B=3 audios decoded together give the tokens of the B=1 runs.  mega: B=1 on the persistent kernel, B=3 on the per-op GEMV
+    kernels (same fp32 activations); perop: both on the GEMV kernels; batched: both on the tensor-core step (a row of the MMA tile
+    does not depend on its neighbours)."""
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
 
     if path == "perop":
         monkeypatch.setenv("BW_NO_MEGA", "1")
+    if path == "batched":
+        monkeypatch.setenv("BW_NO_MEGA", "1")
+        monkeypatch.setenv("BW_BATCH_MIN", "1")
+    else:
+        monkeypatch.setenv("BW_BATCH_MIN", "1000")
 
     meta, gold, model = _model_case("tiny10")
     eng = _engine(model, 10, max_audios=3)

@@ -16,45 +16,28 @@ def _clean(programs, G, seed, prep=None):
     return sim.errors
 
 
-def test_decode_mega3_protocol_is_race_free():
+def test_decode_mega_protocol_is_race_free():
+    """The shipped protocol: 8 grid barriers per layer (tools/protocol_sim.py also models the round-1 experiments -- per-head
+    counters, producer-only arrival, the fused third generation -- which were measured and removed in round 2)."""
     import protocol_sim as ps
 
     G, D, H, ffn, ns, L = 20, 256, 4, 320, 4, 2
-
-    def prep(sim):
-        sim.write(0, "accA", range(D), "zeroA@start")
-        sim.write(0, "accB", range(D), "zeroB@start")
-        sim.vc = [list(sim.vc[0]) for _ in range(G)]
-
-    for seed in range(2):
-        assert _clean(ps.mega3_programs(G, D, H, ffn, ns, L), G, seed, prep) == []
+    for seed in (7, 8):
+        assert _clean(ps.mega1_programs(G, D, H, ffn, ns, L, False, False), G, seed) == []
 
 
-def test_decode_mega_variants_protocol_is_race_free():
+def test_simulator_catches_a_missing_barrier():
     import protocol_sim as ps
 
     G, D, H, ffn, ns, L = 20, 256, 4, 320, 4, 2
-    for p2p, prod in ((False, False), (True, True)):
-        assert _clean(ps.mega1_programs(G, D, H, ffn, ns, L, p2p, prod), G, 7) == []
-
-
-def test_simulator_catches_a_missing_barrier_and_a_wrong_target():
-    import protocol_sim as ps
-
-    G, D, H, ffn, ns, L = 20, 256, 4, 320, 4, 2
-    P = ps.mega1_programs(G, D, H, ffn, ns, L, True, True)
+    P = ps.mega1_programs(G, D, H, ffn, ns, L, False, False)
     for b in range(G):  # drop the barrier between out-proj (C) and LN2 + cross-q (D) of the first layer
         k, out = 0, []
         for op in P[b]:
             if op[0] == "barrier":
                 k += 1
-                if k == 2:
+                if k == 4:
                     continue
             out.append(op)
         P[b] = out
     assert _clean(P, G, 3) != []
-    P = ps.mega1_programs(G, D, H, ffn, ns, L, True, False)
-    for b in range(G):
-        P[b] = [(op[0], op[1], op[2] + 1) if op[0] == "wait" and op[1][0] == "xq" else op for op in P[b]]
-    errs = _clean(P, G, 3)
-    assert errs and "DEADLOCK" in errs[-1]

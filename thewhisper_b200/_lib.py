@@ -42,6 +42,7 @@ SYMBOLS = {
     "bw_last_error": (C.c_char_p, []),
     "bw_abi_version": (C.c_int, []),
     "bw_device_count": (C.c_int, []),
+    "bw_runtime_flags": (C.c_int, []),
     "bw_engine_create": (C.c_int, [C.POINTER(bw_config), C.POINTER(_P)]),
     "bw_engine_destroy": (None, [_P]),
     "bw_engine_set_tensor": (C.c_int, [_P, C.c_char_p, _P]),
@@ -59,8 +60,11 @@ SYMBOLS = {
     "bw_decode_reorder": (C.c_int, [_P, _P, _P, _P]),
     "bw_decode_beam_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "bw_word_timestamps": (C.c_int, [_P, _I, _I, _I, _F, _P, _P]),
+    "bw_word_timestamps_batch": (C.c_int, [_P, _I, _P, _P, _P, _F, _P, _I, _P]),
     "bw_host_merge_overlapping": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
     "bw_op_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _I, _I, _I, _P]),
+    "bw_op_gemm_splitk": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
+    "bw_op_resid_ln": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bw_op_attn_enc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "bw_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "bw_op_gemv": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _P]),

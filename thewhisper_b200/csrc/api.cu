@@ -24,9 +24,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+int g_pdl = 0;
+static int g_pdl_enabled = -1;  // BW_PDL (default on); cleared if a step with programmatic launches cannot be captured
 
-int word_timestamps_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, int audio, int n_tokens, int num_frames,
-                           float time_precision, float* work, float* out_dev);  // timestamps.cu
+size_t word_timestamps_work_floats(int Ha, int Tcap, int S);  // timestamps.cu
+int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
+                                 float time_precision, float* work, float* out_dev);
 
 namespace {
 
@@ -37,7 +40,6 @@ struct EncLayer {
 struct DecLayer {
   const float *ln1g, *ln1b, *bqkv, *bo, *ln2g, *ln2b, *xbq, *xbv, *xbo, *ln3g, *ln3b, *b1, *b2;
   const bf16 *wqkv, *wo, *xwq, *xwk, *xwv, *xwo, *w1, *w2;
-  const bf16 *wo_hm = nullptr, *xwo_hm = nullptr;  // optional head-major copies [H][D][64] of wo / xwo (decode_mega3)
 };
 
 // Everything a captured step graph bakes in as kernel parameters: a decode that differs in any of these gets its own graph
@@ -59,7 +61,7 @@ struct bw_engine {
   bw_config cfg;
   std::map<std::string, const void*> tensors;
   bool finalized = false;
-  int D, H, S, F, V, Tmax, Spad;
+  int D, H, S, F, V, Vp, Tmax, Spad;
   // resolved weights
   const bf16 *conv1_w = nullptr, *conv2_w = nullptr, *embed = nullptr;
   const float *conv1_b = nullptr, *conv2_b = nullptr, *enc_pos = nullptr, *enc_lnf_g = nullptr, *enc_lnf_b = nullptr;
@@ -81,7 +83,7 @@ struct bw_engine {
   unsigned long long* sel_best = nullptr;
   float *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dq = nullptr, *dh = nullptr, *logits = nullptr, *part_o = nullptr,
         *part_ml = nullptr, *align = nullptr, *lse = nullptr, *ts_work = nullptr, *ts_out = nullptr;
-  int *reorder_tmp = nullptr, *cand_tokens = nullptr;
+  int *reorder_tmp = nullptr, *cand_tokens = nullptr, *ts_items = nullptr;
   float *run_scores = nullptr, *cand_scores = nullptr;
   size_t align_bytes = 0;
   // current decode session
@@ -92,13 +94,14 @@ struct bw_engine {
   cudaGraphExec_t cur_graph = nullptr;
   std::map<cudaGraphExec_t, int> graph_kernels;  // kernel nodes of each captured step graph
   long long step_kernel_launches = 0;            // kernels launched by bw_decode_run so far (graph path)
-  bool no_graph = false, simt = false, no_mega = false;
-  int mega_flags = 0;  // BW_MEGA_FLAGS, re-read at every bw_decode_begin (each value has its own step graph)
-  int mega_variant = 0;  // BW_MEGA_VARIANT: compile-time variant of decode_mega_kernel (decode_mega.cu V_* bits)
-  float* dx2 = nullptr;                    // decode_mega3: second residual-stream buffer
-  unsigned long long *acc_a = nullptr, *acc_b = nullptr;  // decode_mega3: fixed-point out-projection accumulators [D]
-  unsigned long long* mega_ll = nullptr;  // self-validating activation words of the V_RELAXED variant
-  size_t mega_ll_words = 0;
+  bool no_graph = false, simt = false, no_mega = false, no_fused_select = false;  // env switches, read ONCE at engine creation
+  int mega_flags = MEGA_DEFAULT_FLAGS;  // BW_MEGA_FLAGS (experiment switches of the persistent step kernel), read once at engine creation
+  // batched (tensor-core) decoder step: bf16 GEMM operands [Qpad][D] / [Qpad][ffn], split-K partial sums [BSPLIT][Qm][D]
+  bf16 *dbn = nullptr, *dba = nullptr, *dbh = nullptr;
+  float* dpart = nullptr;
+  int batch_min = 3;  // sequences from which a step runs on the tcgen05 path (BW_BATCH_MIN)
+  bool gemm2 = true;  // encoder GEMMs on the CTA-pair kernel (BW_GEMM2=0: first-generation kernel only)
+  long long gemm2_min_rows = 1024;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
   long long* mega_trace = nullptr;
@@ -125,7 +128,12 @@ int need(bw_engine* e, const std::string& name, const T** out) {
 }
 
 int gemm(bw_engine* e, cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi) {
-  return e->simt ? gemm_simt(st, a, W, B, rows, N, K, epi) : gemm_tc(st, a, W, B, rows, N, K, epi, 0);
+  if (e->simt) return gemm_simt(st, a, W, B, rows, N, K, epi);
+  // plain row-major activations of all B items are one [B * rows, K] matrix: the CTA-pair kernel tiles it without per-item tails
+  if (e->gemm2 && a.kwrap >= K && a.pitch == K && a.batch_stride == (long long)rows * K && !epi.pos && gemm_tc2_supported(B * rows, N, K) &&
+      (long long)B * rows >= e->gemm2_min_rows)
+    return gemm_tc2(st, a.base, W, B * rows, N, K, rows, epi, 0);
+  return gemm_tc(st, a, W, B, rows, N, K, epi, 0);
 }
 
 GemmA plainA(const bf16* base, int rows, int K) {
@@ -216,11 +224,94 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
   return 0;
 }
 
+constexpr int BSPLIT = 4;  // split-K of the batched step's residual GEMMs (out-proj, cross out-proj, fc2)
+
+// One decoder step for Q >= 3 sequences on the tensor cores: every projection is a tcgen05 GEMM over the [Q, K] activations
+// (gemm_tc_kernel<32>: 32-column weight tiles so N / 32 CTAs stream the weight matrix once, 8-stage TMA ring), LayerNorm + residual
+// update fused in one small kernel between them, the attention kernels of the per-op path with bf16 outputs.  11 launches per
+// layer in one CUDA graph; weights are read once per step whatever Q is (the GEMV path re-reads L2 per 8 rows and runs
+// 2*Q*params flops on the fp32 pipes: compute-bound from Q ~ 16).
+int step_batched_impl(bw_engine* e, cudaStream_t st);
+int step_batched(bw_engine* e, cudaStream_t st) {
+  // programmatic dependent launch for every kernel of the step (BW_PDL=0: plain stream order)
+  if (g_pdl_enabled < 0) {
+    const char* ev = getenv("BW_PDL");
+    g_pdl_enabled = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  g_pdl = g_pdl_enabled;
+  const int rc = step_batched_impl(e, st);
+  g_pdl = 0;
+  return rc;
+}
+int step_batched_impl(bw_engine* e, cudaStream_t st) {
+  const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
+  const long long self_layer = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
+  const long long cross_layer = (long long)e->cfg.max_audios * H * S * 64;
+  const long long pstride = (long long)e->cfg.max_audios * e->cfg.max_beams * D;
+  auto proj = [&](const bf16* in, int K, const bf16* W, int N, const float* bias, float alpha, int act, float* of32, bf16* obf) {
+    GemmEpi ep = plainEpi(Q, N);
+    ep.bias = bias; ep.alpha = alpha; ep.act = act; ep.out_f32 = of32; ep.out_bf16 = obf;
+    return gemm_tc_split(st, plainA(in, Q, K), W, 1, Q, N, K, ep, 32, 1, 0);
+  };
+  auto proj_split = [&](const bf16* in, int K, const bf16* W, int N, int* used) {
+    GemmEpi ep = plainEpi(Q, N);
+    ep.out_f32 = e->dpart;
+    *used = gemm_tc_ksplit(K, BSPLIT);
+    return gemm_tc_split(st, plainA(in, Q, K), W, 1, Q, N, K, ep, 32, BSPLIT, pstride);
+  };
+  if (int rc = launch_embed(st, e->embed, e->dec_pos, e->tokens, e->pos, e->dx, Q, D, Tmax)) return rc;
+  int ns = 0;                  // partial sums of the previous residual GEMM still to be folded into dx
+  const float* pbias = nullptr;
+  for (size_t l = 0; l < e->dec.size(); ++l) {
+    const DecLayer& L = e->dec[l];
+    bf16* kc = e->self_k + l * self_layer;
+    bf16* vc = e->self_v + l * self_layer;
+    // dx += fc2 partials of layer l-1 (+ b2); LN1 -> dbn
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, pbias, L.ln1g, L.ln1b, e->dbn, Q, D)) return rc;
+    // fused QKV projection (q scaled by dh^-1/2; k has no bias: bqkv holds zeros there), fp32 [Q, 3D]
+    {
+      GemmEpi ep = plainEpi(Q, 3 * D);
+      ep.bias = L.bqkv; ep.out_f32 = e->dqkv;
+      ep.alpha = 0.125f; ep.alpha_cols = D;
+      if (int rc = gemm_tc_split(st, plainA(e->dbn, Q, D), L.wqkv, 1, Q, 3 * D, D, ep, 32, 1, 0)) return rc;
+    }
+    {
+      SelfAttnArgs s;
+      s.qkv = e->dqkv; s.kc = kc; s.vc = vc; s.kc_w = kc; s.vc_w = vc; s.anc = e->use_anc ? e->anc : nullptr; s.out_bf16 = e->dba; s.pos = e->pos;
+      s.H = H; s.D = D; s.Tmax = Tmax;
+      if (int rc = launch_self_attn(st, s, Q)) return rc;
+    }
+    if (int rc = proj_split(e->dba, D, L.wo, D, &ns)) return rc;
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, L.bo, L.ln2g, L.ln2b, e->dbn, Q, D)) return rc;
+    if (int rc = proj(e->dbn, D, L.xwq, D, L.xbq, 0.125f, 0, e->dq, nullptr)) return rc;
+    {
+      CrossAttnArgs c;
+      c.q = e->dq; c.kc = e->cross_k + l * cross_layer; c.vc = e->cross_v + l * cross_layer; c.out_bf16 = e->dba;
+      c.part_o = e->part_o; c.part_ml = e->part_ml; c.counters = e->xcounters;
+      c.S = S; c.H = H; c.D = D; c.G = G; c.pos = e->pos;
+      if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
+        c.align = e->align; c.head_slots = e->head_slots + l * H; c.Ha = e->cfg.n_align_heads;
+        c.Tcap = e->cfg.max_align_steps; c.step_base = e->opts.begin_index;
+      }
+      if (int rc = launch_cross_attn(st, c, A)) return rc;
+    }
+    if (int rc = proj_split(e->dba, D, L.xwo, D, &ns)) return rc;
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, L.xbo, L.ln3g, L.ln3b, e->dbn, Q, D)) return rc;
+    if (int rc = proj(e->dbn, D, L.w1, ffn, L.b1, 1.0f, 1, nullptr, e->dbh)) return rc;
+    if (int rc = proj_split(e->dbh, ffn, L.w2, D, &ns)) return rc;
+    pbias = L.b2;
+  }
+  if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, pbias, e->dec_lnf_g, e->dec_lnf_b, e->dbn, Q, D)) return rc;
+  {  // tied LM head: N = V rounded up to 32 (rows of the embedding beyond V are zero-filled by TMA, the pad columns receive 0)
+    GemmEpi ep = plainEpi(Q, e->Vp);
+    ep.out_f32 = e->logits; ep.n_valid = e->V;
+    if (int rc = gemm_tc_split(st, plainA(e->dbn, Q, D), e->embed, 1, Q, e->Vp, D, ep, 128, 1, 0)) return rc;
+  }
+  return 0;
+}
+
 // one decoder step for all Q sequences (enqueued on st; captured into a CUDA graph by the caller)
-// n_steps > 1 is honoured only by the V_MULTI variant of the persistent kernel (greedy selection fused, one sequence);
-// *done = how many steps were enqueued.
-int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullptr) {
-  if (done) *done = 1;
+int step_impl(bw_engine* e, cudaStream_t st) {
   const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, V = e->V, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
   const long long self_layer0 = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
   const long long cross_layer0 = (long long)e->cfg.max_audios * H * S * 64;
@@ -240,7 +331,7 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
     }
     m.L = (int)e->dec.size(); m.D = D; m.H = H; m.ffn = ffn; m.V = V; m.S = S; m.Tmax = Tmax; m.Q = Q;
     m.embed = e->embed; m.dec_pos = e->dec_pos; m.lnf_g = e->dec_lnf_g; m.lnf_b = e->dec_lnf_b;
-    m.tokens = e->tokens; m.pos = e->pos;
+    m.tokens = e->tokens; m.pos = e->pos; m.ldl = e->Vp;
     m.dx = e->dx; m.dqkv = e->dqkv; m.dattn = e->dattn; m.dq = e->dq; m.dh = e->dh; m.logits = e->logits;
     m.part_o = e->part_o; m.part_ml = e->part_ml; m.xcounters = e->xcounters; m.bar = e->mega_bar;
     int ns = e->num_sms / (Q * H);
@@ -252,28 +343,23 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
       m.align = e->align; m.Ha = e->cfg.n_align_heads; m.Tcap = e->cfg.max_align_steps; m.step_base = e->opts.begin_index;
     }
     m.trace = e->mega_trace;
-    if (!e->opts.timestamp_rules && !getenv("BW_NO_FUSED_SELECT")) {
+    if (!e->opts.timestamp_rules && !e->no_fused_select) {
       m.fuse_select = 1;
       m.suppress_bits = e->sup_bits; m.begin_suppress_bits = e->bsup_bits; m.begin_index = e->opts.begin_index;
       m.eos = e->opts.eos_token; m.pad = e->opts.pad_token; m.finished = e->finished; m.tokens_rw = e->tokens; m.pos_rw = e->pos;
       m.sel_best = e->sel_best; m.sel_ctr = e->sel_ctr;
     }
     m.flags = e->mega_flags;
-    m.variant = e->mega_variant;
-    m.ll = e->mega_ll;
-    m.ll_off_dh = (Q <= 1 ? 1 : 2) * D;
-    m.n_steps = ((m.variant & 32) && m.fuse_select && Q == 1 && n_steps > 1) ? n_steps : 1;
-    m.dx2 = e->dx2; m.acc_a = e->acc_a; m.acc_b = e->acc_b;
-    for (size_t l = 0; l < e->dec.size(); ++l) { m.wo_hm[l] = e->dec[l].wo_hm; m.xwo_hm[l] = e->dec[l].xwo_hm; }
-    int rc = -3;
-    if ((m.flags & 128) && m.fuse_select) rc = launch_decode_mega3(st, m, e->num_sms);
-    if (rc == -3) rc = launch_decode_mega(st, m, e->num_sms);
+    const int rc = launch_decode_mega(st, m, e->num_sms);
     if (rc == 0) {
       mega_done = true;
       select_done = m.fuse_select != 0;
-      if (done) *done = m.n_steps;
     }
     else if (rc != -3) return rc;
+  }
+  if (!mega_done && !e->simt && Q >= e->batch_min) {
+    if (int rc = step_batched(e, st)) return rc;
+    mega_done = true;
   }
   if (!mega_done) {
   if (int rc = launch_embed(st, e->embed, e->dec_pos, e->tokens, e->pos, e->dx, Q, D, Tmax)) return rc;
@@ -359,13 +445,13 @@ int step_impl(bw_engine* e, cudaStream_t st, int n_steps = 1, int* done = nullpt
     g.M = Q - m0;
     g.x = e->dx + (long long)m0 * D; g.ldx = D; g.ln_g = e->dec_lnf_g; g.ln_b = e->dec_lnf_b;
     g.W = e->embed; g.N = V; g.K = D;
-    g.out = e->logits + (long long)m0 * V; g.ldo = V;
+    g.out = e->logits + (long long)m0 * e->Vp; g.ldo = e->Vp;
     if (int rc = launch_gemv(st, g)) return rc;
   }
   }  // !mega_done
   if (select_done) return 0;
   SelectArgs s;
-  s.logits = e->logits; s.V = V; s.Q = Q; s.Tmax = Tmax; s.tokens = e->tokens; s.finished = e->finished; s.pos = e->pos;
+  s.logits = e->logits; s.V = V; s.ldl = e->Vp; s.Q = Q; s.Tmax = Tmax; s.tokens = e->tokens; s.finished = e->finished; s.pos = e->pos;
   s.done_ctr = e->done_ctr; s.suppress_bits = e->sup_bits; s.begin_suppress_bits = e->bsup_bits;
   s.begin_index = e->opts.begin_index; s.eos = e->opts.eos_token; s.pad = e->opts.pad_token;
   s.ts_rules = e->opts.timestamp_rules; s.ts_begin = e->opts.timestamp_begin; s.no_ts = e->opts.no_timestamps_token;
@@ -417,6 +503,7 @@ extern "C" {
 
 const char* bw_last_error(void) { return bw::get_error(); }
 int bw_abi_version(void) { return BW_ABI_VERSION; }
+int bw_runtime_flags(void) { return (g_mega_coop == 1 ? 1 : 0) | (g_pdl_enabled == 1 ? 2 : 0); }
 int bw_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -438,10 +525,24 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
   e->cfg = *cfg;
   e->D = cfg->d_model; e->H = cfg->n_heads; e->S = cfg->max_source_positions; e->F = 2 * e->S; e->V = cfg->vocab;
   e->Tmax = cfg->max_target_positions; e->Spad = (e->S + 7) / 8 * 8;
+  e->Vp = (e->V + 31) / 32 * 32;
+  {
+    const char* bm = getenv("BW_BATCH_MIN");
+    if (bm) e->batch_min = atoi(bm);
+    const char* g2 = getenv("BW_GEMM2");
+    if (g2) e->gemm2 = g2[0] != '0';
+    const char* g2r = getenv("BW_GEMM2_MIN_ROWS");
+    if (g2r) e->gemm2_min_rows = atoll(g2r);
+  }
   const char* ng = getenv("BW_NO_GRAPH");
   e->no_graph = ng && ng[0] == '1';
   const char* nm = getenv("BW_NO_MEGA");
   e->no_mega = nm && nm[0] == '1';
+  e->no_fused_select = getenv("BW_NO_FUSED_SELECT") != nullptr;
+  {
+    const char* fl = getenv("BW_MEGA_FLAGS");
+    if (fl) e->mega_flags = atoi(fl);
+  }
   {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) e->num_sms = sms;
@@ -507,12 +608,6 @@ int bw_engine_finalize(bw_engine* e) {
     NEED(bf16, L.wo, p + "wo") NEED(float, L.bo, p + "bo") NEED(float, L.ln2g, p + "ln2.g") NEED(float, L.ln2b, p + "ln2.b")
     NEED(bf16, L.xwq, p + "xwq") NEED(float, L.xbq, p + "xbq") NEED(bf16, L.xwk, p + "xwk") NEED(bf16, L.xwv, p + "xwv")
     NEED(float, L.xbv, p + "xbv") NEED(bf16, L.xwo, p + "xwo") NEED(float, L.xbo, p + "xbo")
-    {
-      auto it = e->tensors.find(p + "wo_hm");
-      if (it != e->tensors.end()) L.wo_hm = static_cast<const bf16*>(it->second);
-      it = e->tensors.find(p + "xwo_hm");
-      if (it != e->tensors.end()) L.xwo_hm = static_cast<const bf16*>(it->second);
-    }
     NEED(float, L.ln3g, p + "ln3.g") NEED(float, L.ln3b, p + "ln3.b")
     NEED(bf16, L.w1, p + "w1") NEED(float, L.b1, p + "b1") NEED(bf16, L.w2, p + "w2") NEED(float, L.b2, p + "b2")
   }
@@ -541,11 +636,6 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "anc", &e->anc, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "anc_tmp", &e->anc_tmp, (size_t)Qm * Tmax)) return -1;
   if (dalloc(e, "done_ctr", &e->done_ctr, 1)) return -1;
-  if (dalloc(e, "dx2", &e->dx2, (size_t)Qm * D)) return -1;
-  if (dalloc(e, "acc_a", &e->acc_a, (size_t)D + 8)) return -1;
-  if (dalloc(e, "acc_b", &e->acc_b, (size_t)D + 8)) return -1;
-  e->mega_ll_words = (size_t)2 * ((size_t)D + c.ffn) + 64;
-  if (dalloc(e, "mega_ll", &e->mega_ll, e->mega_ll_words)) return -1;
   if (dalloc(e, "mega_bar", &e->mega_bar, 1024)) return -1;  // arrival counter [0] + per-CTA flags [32, 32 + SMs)
   {
     const char* tr = getenv("BW_MEGA_TRACE");
@@ -561,7 +651,14 @@ int bw_engine_finalize(bw_engine* e) {
   if (dalloc(e, "dattn", &e->dattn, (size_t)Qm * D)) return -1;
   if (dalloc(e, "dq", &e->dq, (size_t)Qm * D)) return -1;
   if (dalloc(e, "dh", &e->dh, (size_t)Qm * c.ffn)) return -1;
-  if (dalloc(e, "logits", &e->logits, (size_t)Qm * V)) return -1;
+  if (dalloc(e, "logits", &e->logits, (size_t)Qm * e->Vp)) return -1;
+  {
+    const size_t qpad = ((size_t)Qm + 127) / 128 * 128;  // whole 128-row TMA boxes
+    if (dalloc(e, "dbn", &e->dbn, qpad * D)) return -1;
+    if (dalloc(e, "dba", &e->dba, qpad * D)) return -1;
+    if (dalloc(e, "dbh", &e->dbh, qpad * c.ffn)) return -1;
+    if (dalloc(e, "dpart", &e->dpart, (size_t)BSPLIT * Qm * D)) return -1;
+  }
   if (dalloc(e, "lse", &e->lse, (size_t)Qm)) return -1;
   if (dalloc(e, "run_scores", &e->run_scores, (size_t)Qm)) return -1;
   if (dalloc(e, "cand_scores", &e->cand_scores, (size_t)Qm * 16)) return -1;
@@ -581,8 +678,9 @@ int bw_engine_finalize(bw_engine* e) {
   if (c.n_align_heads > 0) {
     BW_CHECK((int)e->align_pairs.size() == 2 * c.n_align_heads, "alignment heads not set");
     if (dalloc(e, "align", &e->align, (size_t)A * c.n_align_heads * c.max_align_steps * S)) return -1;
-    if (dalloc(e, "ts_work", &e->ts_work, (size_t)2 * c.n_align_heads * c.max_align_steps * S + (size_t)(c.max_align_steps + 2) * (S + 2) * 3 + 4096)) return -1;
-    if (dalloc(e, "ts_out", &e->ts_out, (size_t)c.max_align_steps + 8)) return -1;
+    if (dalloc(e, "ts_work", &e->ts_work, (size_t)A * word_timestamps_work_floats(c.n_align_heads, c.max_align_steps, S), false)) return -1;
+    if (dalloc(e, "ts_out", &e->ts_out, (size_t)A * (c.max_align_steps + 8))) return -1;
+    if (dalloc(e, "ts_items", &e->ts_items, (size_t)A * 3)) return -1;
   }
   e->finalized = true;
   return 0;
@@ -645,24 +743,13 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
   BW_CUDA_OK(cudaMemsetAsync(e->pos, 0, sizeof(int), st));
   BW_CUDA_OK(cudaMemsetAsync(e->done_ctr, 0, sizeof(unsigned), st));
   BW_CUDA_OK(cudaMemsetAsync(e->xcounters, 0, sizeof(unsigned) * e->cfg.max_audios * e->H, st));
-  BW_CUDA_OK(cudaMemsetAsync(e->mega_ll, 0, sizeof(unsigned long long) * e->mega_ll_words, st));  // tags restart with the position
-  BW_CUDA_OK(cudaMemsetAsync(e->acc_a, 0, sizeof(unsigned long long) * e->D, st));
-  BW_CUDA_OK(cudaMemsetAsync(e->acc_b, 0, sizeof(unsigned long long) * e->D, st));
   iota_anc_kernel<<<(Q * Tmax + 255) / 256, 256, 0, st>>>(e->anc, Q, Tmax);
   BW_CUDA_OK(cudaGetLastError());
   BW_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
   e->cur_graph = nullptr;
-  {  // experiment switches are re-read per decode so one process can A/B them (tools/mega_ab.py)
-    const char* fl = getenv("BW_MEGA_FLAGS");
-    e->mega_flags = fl ? atoi(fl) : MEGA_DEFAULT_FLAGS;
-    const char* vr = getenv("BW_MEGA_VARIANT");
-    e->mega_variant = vr ? atoi(vr) : 0;
-    const char* nm = getenv("BW_NO_MEGA");
-    e->no_mega = nm && nm[0] == '1';
-  }
   if (!e->no_graph) {
     GraphKey key{A, G, opts->begin_index, opts->timestamp_rules * 4 + (opts->max_initial_timestamp_index + 1) * 8, opts->record_alignment,
-                 e->mega_flags * 4 + e->mega_variant * 65536 + (e->no_mega ? 1 : 0) + (getenv("BW_NO_FUSED_SELECT") ? 2 : 0),
+                 e->mega_flags * 4 + (e->no_mega ? 1 : 0) + (e->no_fused_select ? 2 : 0),
                  opts->eos_token, opts->pad_token, opts->timestamp_begin, opts->no_timestamps_token};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
@@ -677,8 +764,10 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
         if (graph) cudaGraphDestroy(graph);
         graph = nullptr;
         cudaGetLastError();
-        if (attempt == 0 && g_mega_coop == 1) {  // a driver that cannot capture a cooperative launch: plain launch, as in round 1
+        if (attempt == 0 && (g_mega_coop == 1 || g_pdl_enabled == 1)) {
+          // a driver that cannot capture a cooperative / programmatic launch: plain launches, as in round 1
           g_mega_coop = 0;
+          g_pdl_enabled = 0;
           continue;
         }
         cudaStreamDestroy(cs);
@@ -713,17 +802,6 @@ int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, i
 int bw_decode_run(bw_engine* e, int32_t n_steps, void* stream) {
   BW_CHECK(e && e->finalized && e->Q > 0, "bw_decode_run: no decode in progress");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((e->mega_variant & 32) && !e->no_mega && e->G == 1 && e->Q == 1) {
-    // V_MULTI: up to 32 decoder steps per launch, enqueued directly (one memset + one kernel per chunk)
-    for (int i = 0; i < n_steps;) {
-      int done = 1;
-      const int want = n_steps - i < 32 ? n_steps - i : 32;
-      if (int rc = step_impl(e, st, want, &done)) return rc;
-      e->step_kernel_launches += 1;
-      i += done;
-    }
-    return 0;
-  }
   for (int i = 0; i < n_steps; ++i) {
     if (e->cur_graph) {
       BW_CUDA_OK(cudaGraphLaunch(e->cur_graph, st));
@@ -776,20 +854,37 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
   return 0;
 }
 
+int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
+                             float time_precision, float* out_host, int32_t out_pitch, void* stream) {
+  BW_CHECK(e && e->finalized && audio && n_tokens && num_frames && out_host, "bw_word_timestamps_batch: bad arguments");
+  BW_CHECK(e->cfg.n_align_heads > 0 && e->align, "bw_word_timestamps: engine built without alignment heads");
+  BW_CHECK(n >= 1 && n <= e->cfg.max_audios, "bw_word_timestamps_batch: n=%d outside 1..%d", n, e->cfg.max_audios);
+  const int Tcap = e->cfg.max_align_steps;
+  std::vector<int> items((size_t)n * 3);
+  int maxT = 0, maxNF = 0;
+  for (int i = 0; i < n; ++i) {
+    BW_CHECK(audio[i] >= 0 && audio[i] < e->cfg.max_audios, "bw_word_timestamps: audio index out of range");
+    BW_CHECK(n_tokens[i] >= 1 && n_tokens[i] <= Tcap, "bw_word_timestamps: n_tokens=%d outside 1..%d", n_tokens[i], Tcap);
+    BW_CHECK(num_frames[i] >= 1 && num_frames[i] <= e->S, "bw_word_timestamps: num_frames=%d outside 1..%d", num_frames[i], e->S);
+    BW_CHECK(out_pitch >= n_tokens[i] + 1, "bw_word_timestamps_batch: out_pitch=%d too small for %d tokens", out_pitch, n_tokens[i]);
+    items[3 * i] = audio[i]; items[3 * i + 1] = n_tokens[i]; items[3 * i + 2] = num_frames[i];
+    maxT = n_tokens[i] > maxT ? n_tokens[i] : maxT;
+    maxNF = num_frames[i] > maxNF ? num_frames[i] : maxNF;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BW_CUDA_OK(cudaMemcpyAsync(e->ts_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (int rc = word_timestamps_batch_device(st, e->align, e->cfg.n_align_heads, Tcap, e->S, e->ts_items, n, maxT, maxNF, time_precision,
+                                            e->ts_work, e->ts_out))
+    return rc;
+  BW_CUDA_OK(cudaMemcpy2DAsync(out_host, (size_t)out_pitch * sizeof(float), e->ts_out, (size_t)(Tcap + 8) * sizeof(float),
+                               (size_t)(maxT + 1) * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+  BW_CUDA_OK(cudaStreamSynchronize(st));  // `items` goes out of scope; the caller reads out_host
+  return 0;
+}
+
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision, float* out_host,
                        void* stream) {
-  BW_CHECK(e && e->finalized && out_host, "bw_word_timestamps: bad arguments");
-  BW_CHECK(e->cfg.n_align_heads > 0 && e->align, "bw_word_timestamps: engine built without alignment heads");
-  BW_CHECK(audio >= 0 && audio < e->cfg.max_audios, "bw_word_timestamps: audio index out of range");
-  BW_CHECK(n_tokens >= 1 && n_tokens <= e->cfg.max_align_steps, "bw_word_timestamps: n_tokens=%d outside 1..%d", n_tokens, e->cfg.max_align_steps);
-  BW_CHECK(num_frames >= 1 && num_frames <= e->S, "bw_word_timestamps: num_frames=%d outside 1..%d", num_frames, e->S);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int rc = word_timestamps_device(st, e->align, e->cfg.n_align_heads, e->cfg.max_align_steps, e->S, audio, n_tokens, num_frames,
-                                      time_precision, e->ts_work, e->ts_out))
-    return rc;
-  BW_CUDA_OK(cudaMemcpyAsync(out_host, e->ts_out, sizeof(float) * (n_tokens + 1), cudaMemcpyDeviceToHost, st));
-  BW_CUDA_OK(cudaStreamSynchronize(st));
-  return 0;
+  return bw_word_timestamps_batch(e, 1, &audio, &n_tokens, &num_frames, time_precision, out_host, n_tokens + 1, stream);
 }
 
 // ---- single ops -------------------------------------------------------------------------------------------------
@@ -803,7 +898,25 @@ int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, co
   const GemmA a = plainA(static_cast<const bf16*>(A), M, K);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == 1) return gemm_simt(st, a, static_cast<const bf16*>(W), 1, M, N, K, ep);
+  if (impl == 2) return gemm_tc2(st, static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, M, ep, force_bn);
   return gemm_tc(st, a, static_cast<const bf16*>(W), 1, M, N, K, ep, force_bn);
+}
+
+int bw_op_gemm_splitk(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t n_valid, int32_t ksplit, int32_t force_bn,
+                      float* out_partials, int32_t* ksplit_used, void* stream) {
+  BW_CHECK(A && W && out_partials && ksplit_used, "bw_op_gemm_splitk: null pointer");
+  GemmEpi ep = plainEpi(M, N);
+  ep.out_f32 = out_partials;
+  ep.n_valid = (n_valid > 0 && n_valid < N) ? n_valid : 0;
+  *ksplit_used = gemm_tc_ksplit(K, ksplit);
+  return gemm_tc_split(static_cast<cudaStream_t>(stream), plainA(static_cast<const bf16*>(A), M, K), static_cast<const bf16*>(W), 1, M, N, K, ep,
+                       force_bn, ksplit, (long long)M * N);
+}
+
+int bw_op_resid_ln(float* x, const float* partials, int32_t nsplit, const float* bias, const float* ln_g, const float* ln_b, void* y_bf16,
+                   int32_t Q, int32_t D, void* stream) {
+  BW_CHECK(x && (nsplit == 0 || partials) && (!y_bf16 || (ln_g && ln_b)), "bw_op_resid_ln: null pointer");
+  return launch_resid_ln(static_cast<cudaStream_t>(stream), x, partials, nsplit, (long long)Q * D, bias, ln_g, ln_b, static_cast<bf16*>(y_bf16), Q, D);
 }
 
 int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int32_t S, int32_t H, int32_t impl, void* stream) {

@@ -74,6 +74,27 @@ __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (the batched decoder step: ~360 kernels per token in one CUDA graph).  A kernel launched with
+// the programmatic-serialization attribute may START while its predecessor still runs: everything that touches memory the
+// predecessor writes (or reads: WAR) comes after pdl_wait(); weights and other constants may be requested before it.
+// pdl_launch() lets the NEXT kernel's CTAs be scheduled early.  Both are no-ops in a kernel launched the plain way.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern int g_pdl;  // host: 1 while a launcher should attach the programmatic-serialization attribute (set by step_batched)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

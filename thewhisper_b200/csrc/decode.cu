@@ -18,6 +18,8 @@ namespace {
 __global__ void embed_kernel(const bf16* __restrict__ E, const float* __restrict__ P, const int* __restrict__ tokens,
                              const int* __restrict__ pos_ptr, float* __restrict__ x, int D, int Tmax) {
   const int q = blockIdx.x;
+  pdl_wait();
+  pdl_launch();
   const int pos = *pos_ptr;
   const int tok = tokens[q * Tmax + pos];
   for (int d = threadIdx.x; d < D; d += blockDim.x)
@@ -56,11 +58,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const SelectArgs a)
   __shared__ int s_i[8];
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_launch();
   const int pos = *a.pos;          // index of the token just consumed
   const int cur_len = pos + 1;     // tokens present; the new token goes to index cur_len
   const bool generating = cur_len >= a.begin_index && cur_len < a.Tmax;
   if (generating) {
-    const float* lg = a.logits + (long long)q * a.V;
+    const float* lg = a.logits + (long long)q * a.ldl;
     const int* seq = a.tokens + q * a.Tmax;
     // ---- mask ranges from the token history (WhisperTimeStampLogitsProcessor, logits_process.py:1995-2033)
     if (threadIdx.x == 0) {
@@ -248,17 +252,96 @@ __global__ void layernorm_rows_kernel(const float* __restrict__ x, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// batched decoder step: residual update from split-K partial sums fused with the LayerNorm that follows it.
+// One CTA per sequence row, values held in registers (D <= 8 * RL_THREADS).
+// ------------------------------------------------------------------------------------------------
+constexpr int RL_THREADS = 256;
+__device__ __forceinline__ float block_sum_rl(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < RL_THREADS / 32; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+__global__ void __launch_bounds__(RL_THREADS) resid_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int nsplit,
+                                                              long long split_stride, const float* __restrict__ bias,
+                                                              const float* __restrict__ g, const float* __restrict__ b,
+                                                              bf16* __restrict__ y, int D) {
+  __shared__ float red[RL_THREADS / 32];
+  const int q = blockIdx.x;
+  pdl_wait();
+  pdl_launch();
+  float* xr = x + (long long)q * D;
+  float4 v[2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = (threadIdx.x + i * RL_THREADS) * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + k);
+      if (nsplit > 0) {
+        if (bias) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + k);
+          v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+        }
+        for (int sp = 0; sp < nsplit; ++sp) {
+          const float4 pp = *reinterpret_cast<const float4*>(part + (long long)sp * split_stride + (long long)q * D + k);
+          v[i].x += pp.x; v[i].y += pp.y; v[i].z += pp.z; v[i].w += pp.w;
+        }
+        *reinterpret_cast<float4*>(xr + k) = v[i];
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  if (!y) return;
+  const float mean = block_sum_rl(s, red) / (float)D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = (threadIdx.x + i * RL_THREADS) * 4;
+    if (k < D) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  }
+  const float rstd = rsqrtf(block_sum_rl(ss, red) / (float)D + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = (threadIdx.x + i * RL_THREADS) * 4;
+    if (k < D) {
+      const float4 gg = *reinterpret_cast<const float4*>(g + k);
+      const float4 bb = *reinterpret_cast<const float4*>(b + k);
+      uint2 w;
+      w.x = pack_bf16((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+      w.y = pack_bf16((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      *reinterpret_cast<uint2*>(y + (long long)q * D + k) = w;
+    }
+  }
+}
+
 }  // namespace
 
-int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax) {
-  embed_kernel<<<Q, 256, 0, st>>>(E, P, tokens, pos, x, D, Tmax);
-  BW_CUDA_OK(cudaGetLastError());
+int launch_resid_ln(cudaStream_t st, float* x, const float* part, int nsplit, long long split_stride, const float* bias, const float* g,
+                    const float* b, bf16* y, int Q, int D) {
+  BW_CHECK(D % 4 == 0 && D <= 8 * RL_THREADS, "resid_ln: D=%d must be a multiple of 4 and <= %d", D, 8 * RL_THREADS);
+  BW_CUDA_OK(launch_k(resid_ln_kernel, dim3(Q), dim3(RL_THREADS), 0, st, x, part, nsplit, split_stride, bias, g, b, y, D));
   return 0;
 }
 
-int launch_select(cudaStream_t st, const SelectArgs& a) {
-  select_kernel<<<a.Q, SEL_THREADS, 0, st>>>(a);
-  BW_CUDA_OK(cudaGetLastError());
+int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax) {
+  BW_CUDA_OK(launch_k(embed_kernel, dim3(Q), dim3(256), 0, st, E, P, tokens, pos, x, D, Tmax));
+  return 0;
+}
+
+int launch_select(cudaStream_t st, const SelectArgs& a0) {
+  SelectArgs a = a0;
+  if (a.ldl < a.V) a.ldl = a.V;
+  BW_CUDA_OK(launch_k(select_kernel, dim3(a.Q), dim3(SEL_THREADS), 0, st, a));
   return 0;
 }
 

@@ -31,9 +31,14 @@ struct SelfAttnArgs {
   const bf16* kc = nullptr;    // [Q, Tmax, D]
   const bf16* vc = nullptr;
   const int* anc = nullptr;    // [Q, Tmax] sequence slot holding position s for sequence q (null = own slot)
-  float* out = nullptr;        // [Q, D]
+  float* out = nullptr;        // [Q, D] fp32 (per-op GEMV path) ...
+  bf16* out_bf16 = nullptr;    // ... or bf16 (operand of the batched path's tcgen05 out-projection); exactly one of the two
   const int* pos = nullptr;
   int H = 0, D = 0, Tmax = 0;
+  // batched path: the fused QKV GEMM leaves k / v of the current token in qkv (fp32, + bias); the (sequence, head) CTA rounds them to
+  // bf16, appends them to the cache at position *pos and attends over them (the GEMV path appends in its own epilogue)
+  bf16* kc_w = nullptr;
+  bf16* vc_w = nullptr;
 };
 
 constexpr int XSPLIT = 12;   // key splits per (audio, head) in cross attention (<= 128 keys each: S <= 1536)
@@ -43,7 +48,8 @@ struct CrossAttnArgs {
   const float* q = nullptr;  // [Q, D] fp32 (scaled), Q = A*G
   const bf16* kc = nullptr;  // [A, H, S, 64]
   const bf16* vc = nullptr;  // [A, H, S, 64]
-  float* out = nullptr;      // [Q, D]
+  float* out = nullptr;      // [Q, D] fp32, or
+  bf16* out_bf16 = nullptr;  // [Q, D] bf16 (batched path)
   float* part_o = nullptr;   // [A, H, XSPLIT, G, 64]
   float* part_ml = nullptr;  // [A, H, XSPLIT, G, 2]
   unsigned* counters = nullptr;  // [A*H], zero between launches
@@ -57,8 +63,8 @@ struct CrossAttnArgs {
 };
 
 struct SelectArgs {
-  const float* logits = nullptr;  // [Q, V]
-  int V = 0, Q = 0, Tmax = 0;
+  const float* logits = nullptr;  // [Q, ldl], ldl >= V
+  int V = 0, Q = 0, Tmax = 0, ldl = 0;
   int* tokens = nullptr;       // [Q, Tmax]
   int* finished = nullptr;     // [Q]
   int* pos = nullptr;          // device scalar, advanced by the last block
@@ -94,6 +100,7 @@ struct MegaArgs {
   // so no phase spends registers or a dependent global load on it
   MegaLayer layers[MEGA_MAXL];
   int L, D, H, ffn, V, S, Tmax, Q;
+  int ldl;  // row pitch of logits (V rounded up to 32: rows stay 16-byte aligned for the batched path's tcgen05 LM head)
   const bf16* embed;
   const float* dec_pos;
   const float *lnf_g, *lnf_b;
@@ -109,7 +116,7 @@ struct MegaArgs {
   int Ha, Tcap, step_base;
   long long* trace;  // optional barrier timeline (debug)
   int flags;         // bit0: no L2 prefetch two phases ahead; bit1: force single-buffered weight slabs (experiments);
-                     // bit6 (64): the staging warps do not wait for the DMA warp; bit7 (128): decode_mega3.cu
+                     // bit6 (64): the staging warps do not wait for the DMA warp
   // greedy token selection fused behind the LM head (no timestamp rules, one beam): masked arg-max by 64-bit atomicMax,
   // the last CTA to finish writes the token, handles EOS / pad and advances the position -- no select kernel
   int fuse_select;
@@ -122,30 +129,19 @@ struct MegaArgs {
   unsigned long long* sel_best;  // [Q], zero between steps
   unsigned* sel_ctr;             // zero between steps
   int p0_off;        // set by the launcher: byte offset of the second slab region (0: single-buffered slabs)
-  int variant;       // compile-time kernel variant (decode_mega.cu V_* bits; BW_MEGA_VARIANT), 0 = default
-  int n_steps;       // decoder steps in this launch (> 1 only with the V_MULTI variant and fused selection)
-  // decode_mega3.cu (attention fused with its out-projection): head-major copies [H][D][64] of the two out-projection
-  // matrices per layer, the second residual-stream buffer and the two 64-bit fixed-point accumulators [D] (zero between steps)
-  const bf16* wo_hm[MEGA_MAXL];
-  const bf16* xwo_hm[MEGA_MAXL];
-  float* dx2;
-  unsigned long long *acc_a, *acc_b;
-  unsigned long long* ll;  // V_RELAXED: [2 * (D + ffn)] {tag, value} words: dx at 0, dh at ll_off_dh; zeroed by bw_decode_begin
-  int ll_off_dh;
 };
 
 // Returns -3 when the configuration is outside what the persistent kernel supports (caller uses the per-op path).
 int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms);
 extern int g_mega_coop;  // 1: the persistent step kernels are launched cooperatively (co-residency guaranteed by the driver)
-// decode_mega3.cu: attention phases fused with their out-projections, 4 grid barriers per layer; MegaArgs::flags bit 7
-// (BW_MEGA_FLAGS=128) selects it; -3 -> the caller falls back to launch_decode_mega.  (A K-parallel generation,
-// decode_mega2.cu, was measured 3.8 % slower and removed after commit c66a715: profiles/r1_v8_summary.md.)
-int launch_decode_mega3(cudaStream_t st, const MegaArgs& a, int num_sms);
-
 int launch_gemv(cudaStream_t st, const GemvArgs& a);
 int launch_embed(cudaStream_t st, const bf16* E, const float* P, const int* tokens, const int* pos, float* x, int Q, int D, int Tmax);
 int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q);
 int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A);
 int launch_select(cudaStream_t st, const SelectArgs& a);
+// x[q] += bias + sum_{s < nsplit} part[s][q]  (fixed order: deterministic), then y[q] = LayerNorm(x[q]) as bf16.
+// nsplit = 0: LayerNorm only.  part: [nsplit][Q][D] fp32 partial sums of a split-K GEMM (gemm_tc_split).
+int launch_resid_ln(cudaStream_t st, float* x, const float* part, int nsplit, long long split_stride, const float* bias, const float* g,
+                    const float* b, bf16* y, int Q, int D);
 
 }  // namespace bw

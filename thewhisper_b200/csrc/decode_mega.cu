@@ -33,82 +33,22 @@ namespace {
 using namespace mega;
 
 
-// Compile-time variants of the kernel (template parameter VAR, selected per launch by MegaArgs::variant / BW_MEGA_VARIANT).
-// VAR = 0 is the measured default; every other instantiation is a separate kernel, so a variant costs the default nothing
-// (dormant run-time branches did: +2.7 k instructions = +6 %, profiles/r1_v7_experiments.md).
-constexpr unsigned V_NOTRACE = 1;  // trace instrumentation compiled out
-constexpr unsigned V_RELAXED = 2;  // GEMV -> GEMV hand-overs (out-proj -> LN2+cross-q, cross out-proj -> LN3+fc1, fc1 -> fc2, fc2 -> next
-                                   // LN1+QKV / LM head): results travel as {tag, value} 64-bit words, the grid barrier in between
-                                   // has NO release / acquire (red.relaxed + ld.relaxed), the reader validates the tags
-                                   // (sync_bench test 12: 1385 ns against 1621 ns per hand-over)
-constexpr unsigned V_P2P = 4;      // the attention phases wait only for the CTAs that produce THEIR head's q / k / v rows (one
-                                   // counter per head) instead of a grid barrier after LN1+QKV and after LN2+cross-q
-constexpr int P2P_QKV = 256, P2P_XQ = 288;  // word offsets of the per-head counters inside MegaArgs::bar (1024 words, zeroed per launch;
-                                            // the sharded barrier counters live at words 0, 32, 64, 96)
-constexpr unsigned V_SHARD4 = 8;
-constexpr unsigned V_PROD = 16;    // behind the attention phases only their PRODUCERS arrive (20 self-attention CTAs, the 20 CTAs that
-                                   // merged a head's cross-attention partials): one counter per phase kind, everybody polls it --
-                                   // 20 arrivals instead of 148 on the way into both out-projections
-constexpr unsigned V_MULTI = 32;   // MegaArgs::n_steps decoder steps per launch (greedy selection fused): the token and the position travel through
-                                   // global memory behind one extra grid barrier per step; no launch gap, no memset node, no prologue per token
-constexpr int PROD_B = 320, PROD_E = 352;  // word offsets of those counters inside MegaArgs::bar   // grid barrier counter sharded 4 ways (sync_bench: 1253 ns against 1316 ns)
+// Template parameter VAR: bit 0 (V_NOTRACE) compiles the barrier-timeline instrumentation out.  The launcher picks it whenever no
+// trace buffer is attached (-3.6 %: 905 vs 938 us per step, profiles/r2a_variants.md).  Round 1 left five more hand-over variants
+// here (relaxed barriers over tagged activations, per-head readiness counters, a 4-way sharded barrier counter, producer-only
+// arrival, several steps per launch) and a third-generation kernel (attention fused with its out-projection); measured in round 2
+// they were bit-exact and 0.1 % faster to 11 % slower than this one, so they are gone (history: commit c3ab1ae).
+constexpr unsigned V_NOTRACE = 1;
 
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __noinline__ void wait_timeout(const char* what, unsigned a0, unsigned a1) {
   printf("[bw] decode_mega: %s timed out (block %d thread %d: %u %u)\n", what, blockIdx.x, threadIdx.x, a0, a1);
   __trap();
 }
-// ---- self-validating activations (V_RELAXED): one 64-bit word = {tag << 32 | fp32 bits}; 64-bit scalars are single-copy atomic
-__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned tag) {
-  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-// Reads N groups of four consecutive words (32-byte aligned) and re-reads until every tag is >= `tag` (after the relaxed
-// barrier the words are almost always there: 0 late words in 95 M reads of the microbenchmark).  Null groups are skipped.
-template <int N>
-__device__ __forceinline__ void ll_read4(const unsigned long long* const (&p)[N], unsigned tag, float4 (&out)[N]) {
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned long long w[N][4];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (p[i]) {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][0]), "=l"(w[i][1]) : "l"(p[i]) : "memory");
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i][2]), "=l"(w[i][3]) : "l"(p[i] + 2) : "memory");
-      } else {
-        w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0xffffffff00000000ull;
-      }
-    }
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ok = ok && ((unsigned)(w[i][j] >> 32) >= tag);
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        out[i] = p[i] ? make_float4(__uint_as_float((unsigned)w[i][0]), __uint_as_float((unsigned)w[i][1]), __uint_as_float((unsigned)w[i][2]),
-                                    __uint_as_float((unsigned)w[i][3]))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      return;
-    }
-    if (clock64() - t0 > (1ll << 32)) wait_timeout("tagged activation read", tag, 0u);
-  }
-}
-
 // grid barrier: monotonically increasing arrival counter (zeroed by a memset node before the kernel).  bar.sync orders
 // the CTA's writes before thread 0's release; the acquire poll + bar.sync orders the other CTAs' writes before our reads.
 template <unsigned VAR>
 struct GridBar {
   static constexpr bool TRACE = !(VAR & V_NOTRACE);
-  static constexpr bool SHARD = (VAR & V_SHARD4) != 0;
   unsigned* ctr;
   unsigned nblocks;
   unsigned epoch;
@@ -119,38 +59,17 @@ struct GridBar {
   // slice for D <= 1280 and never finishes a row, see prefetch_phase).
   // arrive() right after the CTA's own __syncthreads, wait() after whatever can be requested for the next phase: the arrival
   // is not delayed by the prefetch issue, and the ~700 read requests of a slab copy queue behind the arrival, not before it.
-  // relaxed = true (V_RELAXED hand-overs only): no release / acquire -- everything that crosses this barrier validates itself.
-  __device__ __forceinline__ void arrive(bool relaxed = false) {
+  __device__ __forceinline__ void arrive() {
     if (threadIdx.x == MT - 1) {
       if (TRACE && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2] = global_ns();
-      unsigned* c = SHARD ? ctr + (blockIdx.x & 3u) * 32u : ctr;
-      if ((VAR & V_RELAXED) && relaxed) red_relaxed_add(c, 1u);
-      else red_release_add(c, 1u);
+      red_release_add(ctr, 1u);
     }
   }
   // (a per-CTA flag array polled by one warp instead of the single counter was tried: 3+ us per barrier)
-  __device__ __forceinline__ void wait(bool relaxed = false) {
-    if (SHARD) {
-      if (threadIdx.x >= MT - 4) {
-        const unsigned i = threadIdx.x - (MT - 4);
-        const unsigned cnt = (nblocks > i) ? (nblocks - i + 3u) >> 2 : 0u;  // CTAs b < nblocks with (b & 3) == i
-        const unsigned target = (epoch + 1) * cnt;
-        const long long t0 = clock64();
-        for (;;) {
-          const bool ok = (((VAR & V_RELAXED) && relaxed) ? ld_relaxed_u32(ctr + i * 32u) : ld_acquire_u32(ctr + i * 32u)) >= target;
-          if (__all_sync(0xf0000000u, ok)) break;
-          if (clock64() - t0 > (1ll << 32)) wait_timeout("sharded grid barrier", epoch, i);
-        }
-        if (TRACE && threadIdx.x == MT - 1 && trace && epoch < MEGA_TRACE_N) trace[((long long)blockIdx.x * MEGA_TRACE_N + epoch) * 2 + 1] = global_ns();
-      }
-    } else if (threadIdx.x == MT - 1) {
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == MT - 1) {
       const unsigned target = (epoch + 1) * nblocks;
-      if ((VAR & V_RELAXED) && relaxed) {
-        const long long t0 = clock64();
-        while (ld_relaxed_u32(ctr) < target) {
-          if (clock64() - t0 > (1ll << 32)) wait_timeout("relaxed grid barrier", epoch, 0u);
-        }
-      } else if (ld_acquire_u32(ctr) < target) {
+      if (ld_acquire_u32(ctr) < target) {
         const long long t0 = clock64();
         while (ld_acquire_u32(ctr) < target) {
           if (clock64() - t0 > (1ll << 32)) {
@@ -187,10 +106,6 @@ struct GemvDesc {
   float alpha;            // rows < alpha_cols are scaled (q * 1/sqrt(dh))
   int alpha_cols;
   bf16 *kc, *vc;          // optional self-KV append (fused QKV): rows [D, 2D) -> kc, [2D, 3D) -> vc at position pos
-  // V_RELAXED: where this phase reads its x / publishes its results as {tag, value} words (nullptr: plain fp32 + release barrier)
-  const unsigned long long* ll_in;
-  unsigned long long* ll_out;
-  unsigned tag_in, tag_out;
 };
 
 // g: 0 LN1+QKV | 1 self out-proj | 2 LN2+cross q | 3 cross out-proj | 4 LN3+fc1+GELU | 5 fc2; l == a.L: final LN + LM head
@@ -203,23 +118,6 @@ __device__ __forceinline__ void split_rows(GemvDesc& d) {
 template <unsigned VAR>
 __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer* layers, int l, int g, int pos) {
   GemvDesc d;
-  d.ll_in = nullptr;
-  d.ll_out = nullptr;
-  d.tag_in = d.tag_out = 0u;
-  if (VAR & V_RELAXED) {
-    // tag = ((pos + 1) << 8) + producer phase + 1: strictly increasing within a decode (bw_decode_begin zeroes the words);
-    // phase index = 6 * layer + g, the LM head is phase 6 * L
-    const int ph = l * 6 + g;
-    const unsigned base = ((unsigned)pos + 1u) << 8;
-    d.tag_in = base + (unsigned)ph;  // = tag_out of phase ph - 1
-    d.tag_out = base + (unsigned)ph + 1u;
-    if (g == 2 || g == 4 || (g == 0 && l > 0)) d.ll_in = a.ll;  // dx published by out-proj / cross out-proj / fc2
-    if (g == 5) d.ll_in = a.ll + a.ll_off_dh;                    // dh published by fc1
-    if (l < a.L) {
-      if (g == 1 || g == 3 || g == 5) d.ll_out = a.ll;
-      if (g == 4) d.ll_out = a.ll + a.ll_off_dh;
-    }
-  }
   d.lng = d.lnb = nullptr;
   d.residual = nullptr;
   d.act = 0;
@@ -229,7 +127,7 @@ __device__ __forceinline__ GemvDesc make_desc(const MegaArgs& a, const MegaLayer
   d.N = d.K = d.ldo = a.D;
   d.lm = false;
   if (l >= a.L) {
-    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.n0 = 0; d.nend = a.V; d.lm = true; d.src = a.dx; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.V;
+    d.W = a.embed; d.bias = nullptr; d.N = a.V; d.R = 2; d.n0 = 0; d.nend = a.V; d.lm = true; d.src = a.dx; d.lng = a.lnf_g; d.lnb = a.lnf_b; d.out = a.logits; d.ldo = a.ldl;
     return d;
   }
   const MegaLayer& L = layers[l];
@@ -330,23 +228,12 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
     constexpr int U = 4;
     for (int base = threadIdx.x * 4; base < MB * K; base += ST * 4 * U) {
       float4 v[U];
-      if ((VAR & V_RELAXED) && d.ll_in) {
-        const unsigned long long* pp[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * ST * 4;
-          const int m = (MB > 1 && i >= K) ? 1 : 0;
-          pp[u] = (i < MB * K && m < M) ? d.ll_in + i : nullptr;
-        }
-        ll_read4<U>(pp, d.tag_in, v);
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * ST * 4;
-          const int m = (MB > 1 && i >= K) ? 1 : 0;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
-        }
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * ST * 4;
+        const int m = (MB > 1 && i >= K) ? 1 : 0;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < MB * K && m < M) v[u] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + (i - m * K)));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -362,17 +249,10 @@ __device__ __forceinline__ void stage_x(float* xs, float* red, const GemvDesc& d
   const int k = threadIdx.x * 4;
   const bool have = k < K;
   float4 v[MB];
-  if ((VAR & V_RELAXED) && d.ll_in) {
-    const unsigned long long* pp[MB];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) pp[m] = (have && m < M) ? d.ll_in + (long long)m * K + k : nullptr;
-    ll_read4<MB>(pp, d.tag_in, v);
-  } else {
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
-    }
+  for (int m = 0; m < MB; ++m) {
+    v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have && m < M) v[m] = __ldcg(reinterpret_cast<const float4*>(d.src + (long long)m * K + k));
   }
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
@@ -434,43 +314,12 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
     if (d.act == 1) v = gelu_erf(v);
     if (d.residual) v += res_valid ? res : __ldcg(d.residual + (long long)m * d.ldo + nn);
     d.out[(long long)m * d.ldo + nn] = v;
-    if ((VAR & V_RELAXED) && d.ll_out) ll_store(d.ll_out + (long long)m * d.ldo + nn, v, d.tag_out);
     if (d.kc && nn >= D) {
       const long long row = ((long long)m * Tmax + pos) * D;
       if (nn < 2 * D) d.kc[row + nn - D] = __float2bfloat16(v);
       else d.vc[row + nn - 2 * D] = __float2bfloat16(v);
     }
   }
-}
-
-// ---- V_P2P: per-head readiness counters instead of a grid barrier in front of the attention phases -------------------------
-// A CTA's rows [n0, nend) of a projection whose output is `nblk` blocks of D rows (QKV: q | k | v, cross-q: one block) touch
-// at most two 64-row head ranges (it owns fewer than 64 rows): it signals those heads.  Head h of layer l is ready when its
-// counter reaches (l + 1) * (number of CTAs whose rows intersect one of its ranges); the counters are zeroed with the
-// barrier words before every launch.
-__device__ __forceinline__ void p2p_signal(unsigned* ctr, int n0, int nend, int D) {
-  if (threadIdx.x == MT - 1 && n0 < nend) {
-    const int h0 = (n0 % D) >> 6, h1 = ((nend - 1) % D) >> 6;
-    red_release_add(ctr + h0, 1u);
-    if (h1 != h0) red_release_add(ctr + h1, 1u);
-  }
-}
-__device__ __forceinline__ unsigned p2p_expected(int h, int D, int nblk, int rc) {
-  unsigned n = 0;
-  for (int b = 0; b < nblk; ++b) {
-    const int s0 = b * D + h * 64;
-    n += (unsigned)((s0 + 63) / rc - s0 / rc + 1);
-  }
-  return n;
-}
-__device__ __forceinline__ void p2p_wait(const unsigned* ctr, unsigned target) {
-  if (threadIdx.x == MT - 1 && ld_acquire_u32(ctr) < target) {
-    const long long t0 = clock64();
-    while (ld_acquire_u32(ctr) < target) {
-      if (clock64() - t0 > (1ll << 32)) wait_timeout("head readiness counter", target, ld_acquire_u32(ctr));
-    }
-  }
-  __syncthreads();
 }
 
 // smem carve-up (dynamic): red [64] | xs [MB*ffn] | pool: weight slabs from 0, attention scratch from ATT_OFF
@@ -522,12 +371,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   }
   __syncthreads();
 
-  const int nsteps = (VAR & V_MULTI) ? a.n_steps : 1;
-  for (int step = 0; step < nsteps; ++step) {
-  // (V_MULTI: the previous step's last CTA wrote the token and advanced the position before it arrived at the barrier that
-  // ends a step, so both are read from L2 here)
-  const int pos = ((VAR & V_MULTI) && step > 0) ? __ldcg(a.pos) : pos0;
-  const int lbase = step * a.L;  // the per-head / per-phase-kind counters count layers across the steps of a launch
+  const int pos = pos0;
   // ---- phase 0: embedding (CTA 0 writes the residual stream); first QKV rows + LN1 params requested meanwhile
   GemvDesc cur = make_desc<VAR>(a, sl, 0, 0, pos);
   Pre pre;
@@ -542,7 +386,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
-      const int tok = (VAR & V_MULTI) ? __ldcg(a.tokens + q * a.Tmax + pos) : a.tokens[q * a.Tmax + pos];
+      const int tok = a.tokens[q * a.Tmax + pos];
       a.dx[i] = __bfloat162float(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
     }
   }
@@ -608,12 +452,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
     __syncthreads();  // every warp is done with its slab and with xs: the pool can be re-carved
-    // how this phase's results are handed over (decided before `cur` moves on to the next phase)
-    const bool relaxed_ho = (VAR & V_RELAXED) && cur.ll_out != nullptr;  // self-validating words: barrier without release / acquire
-    const bool p2p_ho = (VAR & V_P2P) && (g == 0 || g == 2);             // per-head counters: no grid barrier at all
-    unsigned* const p2p_ctr = a.bar + (g == 0 ? P2P_QKV : P2P_XQ);
-    if (p2p_ho) p2p_signal(p2p_ctr, cur.n0, cur.nend, D);
-    else bar.arrive(relaxed_ho);
+    bar.arrive();
     if (mkbase && threadIdx.x == 0 && bar.epoch < MEGA_TRACE_N) {
       long long t0 = 0, t1 = 0;
       for (int w = 0; w < MW; ++w) {
@@ -639,11 +478,10 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           cp_async16m(sV + s * 128 + sub * 16, L.self_v + off);
         }
       }
-      if (!(VAR & V_P2P)) bar.wait();
+      bar.wait();
       // ---------------- B: causal self-attention, one (sequence, head) per CTA ----------------
       for (int item = blockIdx.x; item < Q * H; item += gridDim.x) {
         const int q = item / H, h = item - q * H;
-        if (VAR & V_P2P) p2p_wait(a.bar + P2P_QKV + h, (unsigned)(lbase + l + 1) * p2p_expected(h, D, 3, (3 * D + (int)gridDim.x - 1) / (int)gridDim.x));
         const int n = pos + 1;
         uint8_t* sK = att;
         uint8_t* sV = att + (size_t)MAXKEYS * 128;
@@ -668,10 +506,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
         if (threadIdx.x < 64) a.dattn[(long long)q * D + h * 64 + threadIdx.x] = ov / sum;
         fence_proxy_async_smem();  // this thread's scratch writes (generic proxy) before later TMA writes to the same bytes
         __syncthreads();
-        if ((VAR & V_PROD) && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_B, 1u);
       }
-      if (VAR & V_PROD) p2p_wait(a.bar + PROD_B, (unsigned)(lbase + l + 1) * (unsigned)(Q * H));
-      else bar.sync();
+      bar.sync();
     } else if (g == 2) {
       // the encoder K/V slice of this CTA's first cross-attention item is constant during decoding: request it now
       // (contiguous in the head-major cross cache: one bulk copy each)
@@ -686,7 +522,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           bulk_g2s(att + XKMAX * 128, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
         }
       }
-      if (!(VAR & V_P2P)) bar.wait();
+      bar.wait();
       // ---------------- E: cross-attention, (audio, head, key split) items; last split of a head merges ----------------
       {
         uint8_t* sK = att;
@@ -705,7 +541,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
               bulk_g2s(sV, L.cross_v + (((long long)q * H + h) * a.S + s0) * 64, (uint32_t)n * 128, &xbar);
             }
           }
-          if (VAR & V_P2P) p2p_wait(a.bar + P2P_XQ + h, (unsigned)(lbase + l + 1) * p2p_expected(h, D, 1, (D + (int)gridDim.x - 1) / (int)gridDim.x));
           float qv[8];
           {
             const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.dq + (long long)q * D + h * 64 + sub * 8));
@@ -769,13 +604,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
           }
           fence_proxy_async_smem();
           __syncthreads();
-          if ((VAR & V_PROD) && s_last && threadIdx.x == MT - 1) red_release_add(a.bar + PROD_E, 1u);  // this CTA merged (q, h)
         }
       }
-      if (VAR & V_PROD) p2p_wait(a.bar + PROD_E, (unsigned)(lbase + l + 1) * (unsigned)(Q * H));
-      else bar.sync();
+      bar.sync();
     } else {
-      bar.wait(relaxed_ho);
+      bar.wait();
     }
   }
 
@@ -862,8 +695,6 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
       }
     }
   }
-  if ((VAR & V_MULTI) && step + 1 < nsteps) bar.sync();  // the token and the position of the next step are in global memory
-  }  // step
   if (TRACE && a.trace && bar.epoch < MEGA_TRACE_N) {  // end of this CTA's LM-head share
     __syncthreads();
     if (threadIdx.x == 0) a.trace[((long long)blockIdx.x * MEGA_TRACE_N + bar.epoch) * 2] = global_ns();
@@ -887,9 +718,6 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   }
   (void)GW;
   if (a.nsplit > XSPLIT) return -3;
-  if (a.variant != 0 && a.trace && (a.variant & (int)V_NOTRACE)) return -3;  // tracing needs the instrumented instantiation
-  if ((a.variant & (int)V_P2P) && (a.H > 32 || Q * a.H > num_sms)) return -3;
-  if (a.n_steps > 1 && !((a.variant & (int)V_MULTI) && a.fuse_select && Q <= 1)) return -3;  // several steps per launch: V_MULTI only
   const int mb = Q <= 1 ? 1 : 2;
   MegaArgs b = a;
   const size_t smem = mega_smem_plan(mb, a.D, a.ffn, num_sms, !(a.flags & 2), &b.p0_off);
@@ -898,7 +726,6 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
   const int ks = (a.S + a.nsplit - 1) / a.nsplit;
   if (ks > XKMAX) return -3;
   BW_CUDA_OK(cudaMemsetAsync(a.bar, 0, 1024 * sizeof(unsigned), st));
-  // MegaArgs::variant picks a compile-time variant (see V_* at the top); two sequences always run the default
   // Co-residency of the 148 CTAs (round-1 advisor): the grid barriers spin, so a CTA that is not scheduled deadlocks the rest until
   // the 2^32-cycle timeout traps.  (1) the occupancy calculator must promise one CTA per SM, else -3 (per-op path); (2) the launch is
   // cooperative, so the driver either runs the whole grid at once or fails the launch (another kernel holding SMs: an error code at
@@ -925,26 +752,11 @@ int launch_decode_mega(cudaStream_t st, const MegaArgs& a, int num_sms) {
     cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;                                                                           \
     BW_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel<MB, VAR>, b));                                                  \
   }
+  // the instrumented instantiation only when a trace buffer is attached (BW_MEGA_TRACE=1)
   if (mb == 2) {
-    BW_MEGA_LAUNCH(2, 0u)
+    if (a.trace) BW_MEGA_LAUNCH(2, 0u) else BW_MEGA_LAUNCH(2, V_NOTRACE)
   } else {
-    switch ((unsigned)a.variant) {
-      case 0u: BW_MEGA_LAUNCH(1, 0u) break;
-      case V_NOTRACE: BW_MEGA_LAUNCH(1, V_NOTRACE) break;
-      case V_NOTRACE | V_RELAXED: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED) break;
-      case V_NOTRACE | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_P2P) break;
-      case V_NOTRACE | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_SHARD4) break;
-      case V_NOTRACE | V_RELAXED | V_P2P: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P) break;
-      case V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_SHARD4) break;
-      case V_NOTRACE | V_MULTI: BW_MEGA_LAUNCH(1, V_NOTRACE | V_MULTI) break;
-      case V_NOTRACE | V_RELAXED | V_P2P | V_PROD | V_MULTI: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_PROD | V_MULTI) break;
-      case V_NOTRACE | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_PROD) break;
-      case V_NOTRACE | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_P2P | V_PROD) break;
-      case V_NOTRACE | V_RELAXED | V_P2P | V_PROD: BW_MEGA_LAUNCH(1, V_NOTRACE | V_RELAXED | V_P2P | V_PROD) break;
-      default:
-        set_error("decode_mega: variant %d is not instantiated", a.variant);
-        return -1;
-    }
+    if (a.trace) BW_MEGA_LAUNCH(1, 0u) else BW_MEGA_LAUNCH(1, V_NOTRACE)
   }
 #undef BW_MEGA_LAUNCH
   BW_CUDA_OK(cudaGetLastError());

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
   __shared__ float red4[4];
   __shared__ float redo[16][64];
   const int h = blockIdx.x, q = blockIdx.y;
+  pdl_wait();
+  pdl_launch();
   const int pos = *a.pos;
   const int n = pos + 1;
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
@@ -233,11 +235,25 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
   uint8_t* sV = dyn + (size_t)a.Tmax * 128;
   float* sc = reinterpret_cast<float*>(dyn + (size_t)a.Tmax * 256);
   // every K and V row of this (sequence, head) is requested now: one DRAM round trip for the whole kernel
-  for (int s = grp; s < n; s += 16) {
+  const int n_cached = a.kc_w ? pos : n;  // batched path: the row of position `pos` comes from qkv, not from the cache
+  for (int s = grp; s < n_cached; s += 16) {
     const int slot = a.anc ? a.anc[q * a.Tmax + s] : q;
     const long long off = ((long long)slot * a.Tmax + s) * a.D + h * 64 + sub * 8;
     cp_async16(sK + s * 128 + sub * 16, a.kc + off);
     cp_async16(sV + s * 128 + sub * 16, a.vc + off);
+  }
+  if (a.kc_w && grp == (pos & 15)) {  // the group that reads row `pos` below appends it: k / v of this step, rounded to bf16
+    const float* kp = a.qkv + (long long)q * 3 * a.D + a.D + h * 64 + sub * 8;
+    const float4 k0 = *reinterpret_cast<const float4*>(kp), k1 = *reinterpret_cast<const float4*>(kp + 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(kp + a.D), v1 = *reinterpret_cast<const float4*>(kp + a.D + 4);
+    uint4 kw, vw;
+    kw.x = pack_bf16(k0.x, k0.y); kw.y = pack_bf16(k0.z, k0.w); kw.z = pack_bf16(k1.x, k1.y); kw.w = pack_bf16(k1.z, k1.w);
+    vw.x = pack_bf16(v0.x, v0.y); vw.y = pack_bf16(v0.z, v0.w); vw.z = pack_bf16(v1.x, v1.y); vw.w = pack_bf16(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(sK + pos * 128 + sub * 16) = kw;
+    *reinterpret_cast<uint4*>(sV + pos * 128 + sub * 16) = vw;
+    const long long off = ((long long)q * a.Tmax + pos) * a.D + h * 64 + sub * 8;  // a sequence's newest row lives in its own slot
+    *reinterpret_cast<uint4*>(a.kc_w + off) = kw;
+    *reinterpret_cast<uint4*>(a.vc_w + off) = vw;
   }
   const float* qp = a.qkv + (long long)q * 3 * a.D + h * 64 + sub * 8;
   float qv[8];
@@ -287,7 +303,8 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
     float o = 0.f;
 #pragma unroll
     for (int g = 0; g < 16; ++g) o += redo[g][threadIdx.x];
-    a.out[(long long)q * a.D + h * 64 + threadIdx.x] = o * inv;
+    if (a.out_bf16) a.out_bf16[(long long)q * a.D + h * 64 + threadIdx.x] = __float2bfloat16(o * inv);
+    else a.out[(long long)q * a.D + h * 64 + threadIdx.x] = o * inv;
   }
 }
 
@@ -317,6 +334,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
   uint8_t* sV = dyn + XK * 128;
   float (*sc)[XK] = reinterpret_cast<float (*)[XK]>(dyn + 2 * XK * 128);
   float (*redo)[GM][64] = reinterpret_cast<float (*)[GM][64]>(dyn + 2 * XK * 128 + GM * XK * sizeof(float));
+  // the encoder K/V of an audio are constant during decoding: requested BEFORE the programmatic-launch wait, so under PDL the
+  // 32 KB of this CTA are in flight while the previous kernel (the cross-q projection) is still finishing
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int kk = i * 16 + grp;
@@ -325,6 +344,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
       cp_async16(sV + kk * 128 + sub * 16, vbase + (long long)kk * 64);
     }
   }
+  pdl_wait();
+  pdl_launch();
   float qv[GM][8];
 #pragma unroll
   for (int g = 0; g < GM; ++g) {
@@ -447,7 +468,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
           o = fmaf(__ldcg(&a.part_o[(hb + (long long)sp * G + g) * 64 + d]), w, o);
         }
       }
-      a.out[(long long)(au * G + g) * a.D + h * 64 + d] = o / L;
+      if (a.out_bf16) a.out_bf16[(long long)(au * G + g) * a.D + h * 64 + d] = __float2bfloat16(o / L);
+      else a.out[(long long)(au * G + g) * a.D + h * 64 + d] = o / L;
     }
   }
   if (threadIdx.x == 0) a.counters[au * a.H + h] = 0u;
@@ -502,8 +524,7 @@ int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q) {
     attr = true;
   }
   BW_CHECK(smem <= 200 * 1024, "self_attn: Tmax=%d too large", a.Tmax);
-  self_attn_kernel<<<dim3(a.H, Q), 128, smem, st>>>(a);
-  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(launch_k(self_attn_kernel, dim3(a.H, Q), dim3(128), smem, st, a));
   return 0;
 }
 
@@ -517,9 +538,8 @@ int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A) {
     BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemG));
     attr = true;
   }
-  if (a.G == 1) cross_attn_kernel<1><<<dim3(XSPLIT, a.H, A), 128, smem1, st>>>(a);
-  else cross_attn_kernel<MAXG><<<dim3(XSPLIT, a.H, A), 128, smemG, st>>>(a);
-  BW_CUDA_OK(cudaGetLastError());
+  if (a.G == 1) BW_CUDA_OK(launch_k(cross_attn_kernel<1>, dim3(XSPLIT, a.H, A), dim3(128), smem1, st, a));
+  else BW_CUDA_OK(launch_k(cross_attn_kernel<MAXG>, dim3(XSPLIT, a.H, A), dim3(128), smemG, st, a));
   return 0;
 }
 

@@ -22,19 +22,25 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
+// BN = 32 is the decoder-step shape (q_len = 1 for up to 128 sequences per tile): the GEMM is a stream over the weight matrix, so
+// the tile is narrow (N / 32 CTAs cover the SMs without split-K for N >= 3840) and the ring is deep (8 stages x 20 KB in
+// flight per SM hide the DRAM latency; one CTA per SM).
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 32) ? 8 : 4;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (BN < 32) ? 32 : BN;  // power of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 128 /*barriers*/;
-  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int MIN_CTAS = (BN == 256 || BN == 32) ? 1 : 2;
 };
 
 struct GemmParams {
   int B, rows, N, K;
   int kwrap;
   int tiles_m;  // per item
+  int ksplit;   // gridDim.z: split z handles k-blocks [z * kper, min(nk, (z + 1) * kper)) and writes its partial sums at
+  int kper;     // out + z * split_stride (no bias / residual: the consumer adds the partials -- deterministic, no atomics)
+  long long split_stride;
   GemmEpi epi;
 };
 
@@ -65,7 +71,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int b = blockIdx.y / p.tiles_m;
   const int t0 = (blockIdx.y % p.tiles_m) * BM;
   const int n0 = blockIdx.x * BN;
-  const int nk = (p.K + BK - 1) / BK;
+  const int nk_all = (p.K + BK - 1) / BK;
+  const int kb0 = (int)blockIdx.z * p.kper;
+  const int nk = min(nk_all, kb0 + p.kper) - kb0;  // >= 1 (the launcher picks ksplit so that every split owns a k-block)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -87,14 +95,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 4) {
     if (lane == 0) {
+      // The weight tiles of the first ring pass do not depend on the previous kernel: under programmatic dependent launch they are
+      // requested before the wait (their DRAM latency runs beside the predecessor's tail); the activations after it.
+      const int npre = nk < C::STAGES ? nk : C::STAGES;
+      for (int kb = 0; kb < npre; ++kb) {
+        mbar_arrive_expect_tx(&full[kb], A_STAGE_BYTES + C::B_STAGE_BYTES);
+        tma_load_2d(sB + kb * C::B_STAGE_BYTES, &tmW, &full[kb], (kb0 + kb) * BK, n0);
+      }
+      pdl_wait();
+      pdl_launch();
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
-        const int k = kb * BK;
+        const int k = (kb0 + kb) * BK;
+        if (kb >= npre) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+          tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full[s], k, n0);
+        }
         tma_load_3d(sA + s * A_STAGE_BYTES, &tmA, &full[s], k % p.kwrap, t0 + k / p.kwrap, b);
-        tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full[s], k, n0);
       }
     }
   } else if (warp == 5) {
@@ -116,13 +135,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ----------------
+    pdl_wait();  // (residual reads / output stores: after the predecessor grid)
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const int t = t0 + warp * 32 + lane;
     const bool row_ok = t < p.rows;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const GemmEpi& e = p.epi;
-    const long long row_off = (long long)b * e.batch_stride + (long long)t * e.row_stride;
+    const long long row_off = (long long)b * e.batch_stride + (long long)t * e.row_stride + (long long)blockIdx.z * p.split_stride;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int n = n0 + c * 32;
@@ -142,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
           }
         }
-        if (e.alpha != 1.0f) {
+        if (e.alpha != 1.0f && n < e.alpha_cols) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= e.alpha;
         }
@@ -204,14 +224,15 @@ __global__ void gemm_simt_kernel(GemmA a, const bf16* __restrict__ W, GemmParams
   const bf16* ab = a.base + (long long)b * a.batch_stride;
   const bf16* w = W + (long long)n * p.K;
   float acc = 0.f;
-  for (int k = 0; k < p.K; ++k) {
+  const int kend = (p.epi.n_valid > 0 && n >= p.epi.n_valid) ? 0 : p.K;  // rows of W beyond n_valid do not exist: zero
+  for (int k = 0; k < kend; ++k) {
     const float av = __bfloat162float(ab[(long long)(t + k / p.kwrap) * a.pitch + (k % p.kwrap)]);
     acc = fmaf(av, __bfloat162float(w[k]), acc);
   }
   const GemmEpi& e = p.epi;
   const long long off = (long long)b * e.batch_stride + (long long)t * e.row_stride + (long long)(n >> 6) * e.head_stride + (n & 63);
   if (e.bias) acc += e.bias[n];
-  acc *= e.alpha;
+  if (n < e.alpha_cols) acc *= e.alpha;
   if (e.act == 1) acc = gelu_erf(acc);
   if (e.pos) acc += e.pos[(long long)t * p.N + n];
   if (e.residual) acc += e.residual[off];
@@ -283,20 +304,34 @@ template <int BN>
 static int launch_tc(cudaStream_t st, const CUtensorMap& tmA, const GemmA& a, const bf16* W, const GemmParams& p) {
   using C = Cfg<BN>;
   CUtensorMap tmW;
-  if (int rc = make_tmap_2d_bf16(&tmW, W, p.N, p.K, (uint64_t)p.K * 2, BN, BK)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmW, W, p.epi.n_valid > 0 ? p.epi.n_valid : p.N, p.K, (uint64_t)p.K * 2, BN, BK)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     BW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, p.tiles_m * p.B);
-  gemm_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, st>>>(tmA, tmW, p);
-  BW_CUDA_OK(cudaGetLastError());
+  dim3 grid((p.N + BN - 1) / BN, p.tiles_m * p.B, p.ksplit);
+  BW_CUDA_OK(launch_k(gemm_tc_kernel<BN>, grid, dim3(192), (size_t)C::SMEM_BYTES, st, tmA, tmW, p));
   return 0;
 }
 
 int gemm_tc(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi, int force_bn) {
+  return gemm_tc_split(st, a, W, B, rows, N, K, epi, force_bn, 1, 0);
+}
+
+int gemm_tc_ksplit(int K, int ksplit) {
+  const int nk = K / BK;
+  if (ksplit > nk) ksplit = nk;
+  if (ksplit < 1) ksplit = 1;
+  const int kper = (nk + ksplit - 1) / ksplit;
+  return (nk + kper - 1) / kper;
+}
+
+int gemm_tc_split(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi, int force_bn,
+                  int ksplit, long long split_stride) {
   if (int rc = check_epi(epi, N)) return rc;
+  BW_CHECK(ksplit >= 1 && (ksplit == 1 || (epi.out_f32 && !epi.bias && !epi.residual && !epi.pos && epi.act == 0 && epi.alpha == 1.0f)),
+           "gemm_tc: split-K writes raw fp32 partial sums (no bias / activation / residual)");
   BW_CHECK(K % 64 == 0, "gemm_tc: K=%d must be a multiple of 64", K);
   BW_CHECK(a.pitch % 8 == 0 && a.batch_stride % 8 == 0, "gemm_tc: A pitch/batch stride must be multiples of 8 elements");
   BW_CHECK(a.kwrap >= K || a.kwrap % 64 == 0, "gemm_tc: kwrap=%d must be a multiple of 64", a.kwrap);
@@ -305,6 +340,12 @@ int gemm_tc(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int
   p.kwrap = a.kwrap >= K ? INT_MAX : a.kwrap;
   p.tiles_m = (rows + BM - 1) / BM;
   p.epi = epi;
+  {
+    const int nk = K / BK;
+    p.ksplit = gemm_tc_ksplit(K, ksplit);  // every split owns >= 1 k-block
+    p.kper = (nk + p.ksplit - 1) / p.ksplit;
+    p.split_stride = split_stride;
+  }
   const uint64_t inner = (uint64_t)(a.kwrap >= K ? K : a.kwrap);
   CUtensorMap tmA;
   if (int rc = make_tmap_3d_bf16(&tmA, a.base, (uint64_t)B, (uint64_t)a.rows_base, inner, (uint64_t)a.pitch * 2,
@@ -318,6 +359,7 @@ int gemm_tc(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int
     if (N < 128) bn = 64;
   }
   switch (bn) {
+    case 32: return launch_tc<32>(st, tmA, a, W, p);
     case 64: return launch_tc<64>(st, tmA, a, W, p);
     case 128: return launch_tc<128>(st, tmA, a, W, p);
     case 256: return launch_tc<256>(st, tmA, a, W, p);
@@ -331,6 +373,7 @@ int gemm_simt(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, i
   p.B = B; p.rows = rows; p.N = N; p.K = K;
   p.kwrap = a.kwrap >= K ? INT_MAX : a.kwrap;
   p.tiles_m = (rows + 15) / 16;
+  p.ksplit = 1; p.kper = 0; p.split_stride = 0;
   p.epi = epi;
   dim3 grid((N + 15) / 16, p.tiles_m * B);
   gemm_simt_kernel<<<grid, dim3(16, 16), 0, st>>>(a, W, p);

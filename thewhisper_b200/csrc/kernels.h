@@ -22,7 +22,8 @@ struct GemmA {
 
 struct GemmEpi {
   const float* bias = nullptr;      // [N] fp32 or null
-  float alpha = 1.0f;               // (acc + bias) * alpha       (q-projection scaling)
+  float alpha = 1.0f;               // (acc + bias) * alpha for columns n < alpha_cols (q-projection scaling; alpha_cols % 32 == 0)
+  int alpha_cols = 0x7fffffff;
   int act = 0;                      // 0 none, 1 exact-erf GELU
   const float* residual = nullptr;  // fp32, same addressing as the output; may alias out_f32 (in-place x += ...)
   const float* pos = nullptr;       // fp32 [rows, N] added after the activation (encoder positional table)
@@ -33,11 +34,22 @@ struct GemmEpi {
   long long batch_stride = 0;
   long long row_stride = 0;
   long long head_stride = 64;
+  int n_valid = 0;  // rows of W that exist in memory (0 = N); rows beyond are zero-filled by TMA (tied LM head: V = 51866 of N = 51872)
 };
 
 // W: [N, K] bf16 row-major (torch Linear layout).  K % 64 == 0, N % 32 == 0.  rows = output rows per item.
 int gemm_tc(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi,
             int force_bn /*0 = auto, else 64/128/256*/);
+// Split-K form for the decoder's residual GEMMs (K >> N / 148 tiles): grid.z = ksplit, split z writes raw fp32 partial sums at
+// out_f32 + z * split_stride; the consumer (resid_ln) adds them in a fixed order.  ksplit is clamped so that every split owns a k-block (gemm_tc_ksplit gives the count used).
+int gemm_tc_split(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi, int force_bn,
+                  int ksplit, long long split_stride);
+int gemm_tc_ksplit(int K, int ksplit);
+// Second-generation encoder GEMM (gemm_tc2.cu): CTA pairs (cta_group::2, 256 x BN tiles), persistent, double-buffered TMEM.
+// A [M, K] plain row-major; the epilogue address map splits the flat row r as b = r / rows_per_item, t = r % rows_per_item
+// (rows_per_item <= 0: one item).  No conv wrap, no positional table.  force_bn: 0 auto, 128, 256.
+bool gemm_tc2_supported(int M, int N, int K);
+int gemm_tc2(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, int K, int rows_per_item, const GemmEpi& epi, int force_bn);
 // CUDA-core sibling with identical semantics: on-device comparator for the tests and the bring-up fallback
 // selected by BW_GEMM_IMPL=simt (never the default).
 int gemm_simt(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi);

@@ -16,10 +16,36 @@ namespace bw {
 
 namespace {
 
+// One descriptor per audio of a batch (blockIdx.z): which alignment block, how many generated tokens / valid frames.
+// Per-item scratch lives at work + z * work_stride (floats), results at out + z * out_stride.
+struct TsBatch {
+  const int* items;  // [n][3] device: audio index, T, NF
+  long long work_stride, out_stride, align_stride;
+  int Ha, Tcap, S;
+};
+struct TsWork {
+  float* probs;
+  float* z;
+  double* negm;
+  signed char* trace;
+};
+__device__ __forceinline__ TsWork ts_work(float* work, const TsBatch& b, int item) {
+  TsWork w;
+  w.probs = work + (long long)item * b.work_stride;
+  w.z = w.probs + (size_t)b.Ha * b.Tcap * b.S;
+  w.negm = reinterpret_cast<double*>(w.z + (size_t)b.Ha * b.Tcap * b.S);
+  w.trace = reinterpret_cast<signed char*>(w.negm + (size_t)b.Tcap * b.S);
+  return w;
+}
+
 // scores [Ha][Tcap][S] (one audio) -> probs [Ha][T][NF] = softmax over all S keys, first NF kept
-__global__ void ts_softmax_kernel(const float* __restrict__ scores, float* __restrict__ probs, int Tcap, int S, int T, int NF) {
+__global__ void ts_softmax_kernel(const float* __restrict__ align, float* __restrict__ work, const TsBatch b) {
   __shared__ float red[32];
-  const int t = blockIdx.x, ha = blockIdx.y;
+  const int t = blockIdx.x, ha = blockIdx.y, item = blockIdx.z;
+  const int audio = b.items[item * 3], T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2], Tcap = b.Tcap, S = b.S;
+  if (t >= T) return;
+  const float* scores = align + (long long)audio * b.align_stride;
+  float* probs = ts_work(work, b, item).probs;
   const float* row = scores + ((long long)ha * Tcap + t) * S;
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < S; j += blockDim.x) mx = fmaxf(mx, row[j]);
@@ -41,9 +67,13 @@ __global__ void ts_softmax_kernel(const float* __restrict__ scores, float* __res
 }
 
 // z-score over the token axis for each (head, frame)
-__global__ void ts_zscore_kernel(const float* __restrict__ probs, float* __restrict__ z, int T, int NF, int Ha) {
+__global__ void ts_zscore_kernel(float* __restrict__ work, const TsBatch b) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ha = blockIdx.y;
+  const int ha = blockIdx.y, item = blockIdx.z;
+  const int T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2];
+  const TsWork w = ts_work(work, b, item);
+  const float* probs = w.probs;
+  float* z = w.z;
   if (j >= NF) return;
   const float* p = probs + (long long)ha * T * NF + j;
   float s = 0.f;
@@ -66,10 +96,14 @@ __device__ __forceinline__ void cswap(float& a, float& b) {
 }
 
 // median-7 along frames (reflect padding), then mean over heads; output NEGATED in double for the DTW
-__global__ void ts_median_mean_kernel(const float* __restrict__ z, double* __restrict__ negm, int T, int NF, int Ha) {
+__global__ void ts_median_mean_kernel(float* __restrict__ work, const TsBatch b) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (j >= NF) return;
+  const int t = blockIdx.y, item = blockIdx.z;
+  const int T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2], Ha = b.Ha;
+  const TsWork w = ts_work(work, b, item);
+  const float* z = w.z;
+  double* negm = w.negm;
+  if (j >= NF || t >= T) return;
   float acc = 0.f;
   for (int ha = 0; ha < Ha; ++ha) {
     const float* row = z + ((long long)ha * T + t) * NF;
@@ -98,10 +132,15 @@ __global__ void ts_median_mean_kernel(const float* __restrict__ z, double* __res
   negm[(long long)t * NF + j] = -(double)m;
 }
 
-// anti-diagonal wavefront DTW for one audio, then a serial backtrace.  One block.
-__global__ void __launch_bounds__(512) ts_dtw_kernel(const double* __restrict__ negm, signed char* __restrict__ trace, int T, int NF,
-                                                      float time_precision, float* __restrict__ out) {
-  extern __shared__ float diag[];  // 3 x (T + 2)
+// anti-diagonal wavefront DTW for one audio, then a serial backtrace.  One block per audio of the batch.
+__global__ void __launch_bounds__(512) ts_dtw_kernel(float* __restrict__ work, const TsBatch b, float time_precision, float* __restrict__ out_all) {
+  extern __shared__ float diag[];  // 3 x (Tcap + 2)
+  const int item = blockIdx.x;
+  const int T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2];
+  const TsWork w = ts_work(work, b, item);
+  const double* negm = w.negm;
+  signed char* trace = w.trace;
+  float* out = out_all + (long long)item * b.out_stride;
   float* d0 = diag;               // diagonal d-2
   float* d1 = diag + (T + 2);     // diagonal d-1
   float* d2 = diag + 2 * (T + 2); // diagonal d
@@ -154,22 +193,28 @@ __global__ void __launch_bounds__(512) ts_dtw_kernel(const double* __restrict__ 
 
 }  // namespace
 
-// work layout (floats): probs [Ha*T*NF] | z [Ha*T*NF] | negm (double) [T*NF] | trace (int8) [(T+1)*(NF+1)]
-int word_timestamps_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, int audio, int n_tokens, int num_frames,
-                           float time_precision, float* work, float* out_dev) {
-  const int T = n_tokens, NF = num_frames;
-  const float* scores = align + (long long)audio * Ha * Tcap * S;
-  float* probs = work;
-  float* z = work + (size_t)Ha * Tcap * S;
-  double* negm = reinterpret_cast<double*>(z + (size_t)Ha * Tcap * S);
-  signed char* trace = reinterpret_cast<signed char*>(negm + (size_t)Tcap * S);
-  ts_softmax_kernel<<<dim3(T, Ha), 256, 0, st>>>(scores, probs, Tcap, S, T, NF);
+// per-item work layout (floats): probs [Ha*Tcap*S] | z [Ha*Tcap*S] | negm (double) [Tcap*S] | trace (int8) [(Tcap+1)*(S+1)]
+size_t word_timestamps_work_floats(int Ha, int Tcap, int S) {
+  const size_t n = (size_t)2 * Ha * Tcap * S + (size_t)2 * Tcap * S + ((size_t)(Tcap + 2) * (S + 2) + 3) / 4 + 64;
+  return (n + 3) / 4 * 4;  // items stay 16-byte aligned (the double section starts at an even float offset)
+}
+
+// n audios in one pass (4 launches whatever n is): items_dev [n][3] = (audio, T, NF); out_dev [n][Tcap + 8] seconds
+int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
+                                 float time_precision, float* work, float* out_dev) {
+  TsBatch b;
+  b.items = items_dev;
+  b.work_stride = (long long)word_timestamps_work_floats(Ha, Tcap, S);
+  b.out_stride = Tcap + 8;
+  b.align_stride = (long long)Ha * Tcap * S;
+  b.Ha = Ha; b.Tcap = Tcap; b.S = S;
+  ts_softmax_kernel<<<dim3(maxT, Ha, n), 256, 0, st>>>(align, work, b);
   BW_CUDA_OK(cudaGetLastError());
-  ts_zscore_kernel<<<dim3((NF + 127) / 128, Ha), 128, 0, st>>>(probs, z, T, NF, Ha);
+  ts_zscore_kernel<<<dim3((maxNF + 127) / 128, Ha, n), 128, 0, st>>>(work, b);
   BW_CUDA_OK(cudaGetLastError());
-  ts_median_mean_kernel<<<dim3((NF + 127) / 128, T), 128, 0, st>>>(z, negm, T, NF, Ha);
+  ts_median_mean_kernel<<<dim3((maxNF + 127) / 128, maxT, n), 128, 0, st>>>(work, b);
   BW_CUDA_OK(cudaGetLastError());
-  ts_dtw_kernel<<<1, 512, 3 * (T + 2) * sizeof(float), st>>>(negm, trace, T, NF, time_precision, out_dev);
+  ts_dtw_kernel<<<n, 512, 3 * (Tcap + 2) * sizeof(float), st>>>(work, b, time_precision, out_dev);
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }

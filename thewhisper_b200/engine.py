@@ -121,10 +121,6 @@ def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, enc_pos: torch.Te
         out[o + "xwv"] = mat(sd[p + "encoder_attn.v_proj.weight"])
         out[o + "xbv"] = vec(sd[p + "encoder_attn.v_proj.bias"])
         out[o + "xwo"] = mat(sd[p + "encoder_attn.out_proj.weight"])
-        # head-major copies [H][D][64] of the two out-projections: the slab of a fused (head, row slice) item of the
-        # third-generation decoder-step kernel (csrc/decode_mega3.cu) is contiguous in them
-        out[o + "wo_hm"] = mat(sd[p + "self_attn.out_proj.weight"].reshape(D, dims.n_heads, 64).permute(1, 0, 2))
-        out[o + "xwo_hm"] = mat(sd[p + "encoder_attn.out_proj.weight"].reshape(D, dims.n_heads, 64).permute(1, 0, 2))
         out[o + "xbo"] = vec(sd[p + "encoder_attn.out_proj.bias"])
         out[o + "ln3.g"] = vec(sd[p + "final_layer_norm.weight"])
         out[o + "ln3.b"] = vec(sd[p + "final_layer_norm.bias"])
@@ -207,6 +203,16 @@ class WhisperEngine:
         torch.cuda.current_stream(self.device).synchronize()
         _lib.device_copy(out.data_ptr(), p.value, n * itemsize)
         return out.view(*shape)
+
+    def write_buffer(self, name: str, src: torch.Tensor, offset_bytes: int = 0) -> None:
+        """Overwrite (part of) an internal device buffer from a device tensor (op-level tests: e.g. alignment scores)."""
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.bw_engine_buffer(self.h, name.encode(), C.byref(p), C.byref(nbytes)))
+        src = src.contiguous()
+        n = src.numel() * src.element_size()
+        assert offset_bytes + n <= nbytes.value, (name, offset_bytes, n, nbytes.value)
+        torch.cuda.current_stream(self.device).synchronize()
+        _lib.device_copy(p.value + offset_bytes, src.data_ptr(), n)
 
     # ------------------------------------------------------------------------------------------
     def logmel(self, pcm: np.ndarray, return_f32: bool = False) -> Optional[torch.Tensor]:
@@ -294,7 +300,8 @@ class WhisperEngine:
         return cs, ct
 
     def logits(self) -> torch.Tensor:
-        return self.buffer("logits", torch.float32, (self.max_audios * self.max_beams, self.dims.vocab))[: self._Q]
+        vp = (self.dims.vocab + 31) // 32 * 32  # row pitch of the engine's logits buffer (rows stay 16-byte aligned)
+        return self.buffer("logits", torch.float32, (self.max_audios * self.max_beams, vp))[: self._Q, : self.dims.vocab]
 
     def greedy(self, prompts: np.ndarray, A: int, opts: DecodeOptions, max_new_tokens: int, poll_every: int = 32):
         """Greedy decode of A audios (their cross K/V must be resident from encode()).  Returns generated ids per
@@ -321,6 +328,20 @@ class WhisperEngine:
             cut = np.where(row == opts.eos_token)[0]
             out.append(row[: cut[0]] if len(cut) else row)
         return out, toks, done
+
+    def word_timestamps_batch(self, audios: Sequence[int], n_tokens: Sequence[int], num_frames: Sequence[int],
+                              time_precision: float = 0.02) -> np.ndarray:
+        """Token times of several audios in one pass -> [n, max(n_tokens) + 1] float32 (rows padded with zeros)."""
+        n = len(audios)
+        au = np.ascontiguousarray(audios, dtype=np.int32)
+        nt = np.ascontiguousarray(n_tokens, dtype=np.int32)
+        nf = np.ascontiguousarray(num_frames, dtype=np.int32)
+        pitch = int(nt.max()) + 1
+        out = np.zeros((n, pitch), dtype=np.float32)
+        _lib.check(self.lib.bw_word_timestamps_batch(self.h, n, au.ctypes.data_as(C.c_void_p), nt.ctypes.data_as(C.c_void_p),
+                                                     nf.ctypes.data_as(C.c_void_p), time_precision, out.ctypes.data_as(C.c_void_p),
+                                                     pitch, self._stream()))
+        return out
 
     def word_timestamps(self, audio: int, n_tokens: int, num_frames: int, time_precision: float = 0.02) -> np.ndarray:
         out = np.zeros(n_tokens + 1, dtype=np.float32)

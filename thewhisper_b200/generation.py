@@ -155,15 +155,14 @@ class WhisperGenerator:
 
     def _token_timestamps(self, A: int, plen: int, n_steps: int, num_frames: np.ndarray) -> List[np.ndarray]:
         """HF layout: zeros for the prompt, one time per generated position, last one duplicated (:375-379)."""
-        out = []
         T = n_steps - 1
-        for a in range(A):
-            ts = np.zeros(plen + n_steps, dtype=np.float32)
-            if T >= 1:
-                nf = max(1, min(int(num_frames[a]) // 2, self.eng.S))
-                jt = self.eng.word_timestamps(a, min(T, self.eng.max_align_steps), nf, self.time_precision)
-                ts[plen:plen + T + 1] = jt[: T + 1]
-            out.append(ts)
+        out = [np.zeros(plen + n_steps, dtype=np.float32) for _ in range(A)]
+        if T >= 1 and A > 0:  # all audios of the batch in one pass of the four timestamp kernels
+            Tc = min(T, self.eng.max_align_steps)
+            nfs = [max(1, min(int(num_frames[a]) // 2, self.eng.S)) for a in range(A)]
+            jt = self.eng.word_timestamps_batch(list(range(A)), [Tc] * A, nfs, self.time_precision)
+            for a in range(A):
+                out[a][plen:plen + Tc + 1] = jt[a, : Tc + 1]
         return out
 
     def _split_segments(self, seq: np.ndarray, time_offset: float, seek_num_frames: int, idx_offset: int,

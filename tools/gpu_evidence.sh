@@ -7,7 +7,6 @@
 #   launches     ncu launch list (gpu__time_duration.sum) of a short bench run
 #   ncu_mega     ncu --set full of the persistent decoder-step kernel
 #   trace        barrier timeline of one decoder step
-#   variants     A/B + parity of every compile-time variant of decode_mega_kernel and of decode_mega3
 #   ncu_encoder  ncu --set full of log-mel / tcgen05 GEMM / tcgen05 attention / LayerNorm
 #   configs      tools/bench_configs.py C3 C5 C4 (BASELINE.json configs bench.py does not time)
 #   ncu_batched  launch list + ncu --set full of the batched decoder step (A = 64)
@@ -40,15 +39,6 @@ for sec in "$@"; do
     tail -1 ${O}_ncu_mega.log; summ ${O}_mega.ncu-rep | tee ${O}_mega_summary.txt ;;
   trace)
     timeout 300 python tools/mega_trace.py 2>&1 | tee ${O}_trace.log | tail -30 ;;
-  variants)
-    BW_AB="${BW_AB:-64:0,64:1,64:3,64:5,64:9,64:17,64:21,64:23,64:33,64:55,64:7,64:15,64:0}" timeout 600 python tools/mega_ab.py 2>&1 | tail -16 | tee ${O}_variants_ab.log
-    for v in ${VARIANT_TESTS:-3 5 17 23 33 55 15}; do
-      echo "== variant $v: model parity tests"
-      BW_MEGA_VARIANT=$v timeout 600 python -m pytest tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -k "teacher_forced or batch_rows" 2>&1 | grep -v Warning | tail -4 | tee ${O}_variants_tests_$v.log
-    done
-    echo "== decode_mega3 (BW_MEGA_FLAGS=192)"
-    BW_MEGA_FLAGS=192 timeout 600 python -m pytest tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -k "teacher_forced or batch_rows" 2>&1 | grep -v Warning | tail -6 | tee ${O}_variants_tests_mega3.log
-    BW_AB="64:0,192:0,192:33,64:0,192:0,192:33" timeout 300 python tools/mega_ab.py 2>&1 | tail -7 | tee ${O}_variants_ab_mega3.log ;;
   ncu_encoder)
     for spec in "gemm_tc:40:4" "attn_enc_tc:8:2" "logmel:2:2" "layernorm_rows:8:2"; do
       IFS=: read -r pat skip cnt <<< "$spec"

@@ -62,20 +62,26 @@ def main():
     preset = os.environ.get("BW_PRESET", "large-v3")
     steps = int(os.environ.get("BW_STEPS", "8"))
     A = int(os.environ.get("BW_A", "1"))
+    G = int(os.environ.get("BW_G", "1"))  # sequences per audio (beams): the step runs A * G rows, cross K/V shared per audio
+    chunk_s = int(os.environ.get("BW_CHUNK_S", "30"))
     dev = torch.device("cuda:0")
     dims = ModelDims.from_hf_config(S.make_hf_config(preset))
     sd = random_state_dict(dims, dev)
     w = pack_weights(sd, dims, sd["model.encoder.embed_positions.weight"], dev)
     del sd
-    eng = WhisperEngine({}, dims, chunk_length_s=30, device="cuda:0", max_audios=A, weights=w)
+    if chunk_s != 30:
+        from thewhisper_b200.engine import interpolate_positions
+
+        w["enc.pos"] = interpolate_positions(w["enc.pos"], chunk_s).to(dev)
+    eng = WhisperEngine({}, dims, chunk_length_s=chunk_s, device="cuda:0", max_audios=A, max_beams=G, weights=w)
     g = S.make_generation_config(preset, eos_suppressed=True)
     opts = DecodeOptions(eos_token=S.EOS, pad_token=S.EOS, suppress_tokens=list(g.suppress_tokens), begin_suppress_tokens=list(g.begin_suppress_tokens))
-    pcm = np.stack([S.synth_audio(30, seed=1000 + i) for i in range(A)])
-    prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]] * A, dtype=np.int32)
+    pcm = np.stack([S.synth_audio(chunk_s, seed=1000 + i) for i in range(A)])
+    prompt = np.array([[S.SOT, S.LANG_EN, S.TRANSCRIBE, S.NOTIMESTAMPS]] * (A * G), dtype=np.int32)
     for it in range(2):
         eng.logmel(pcm)
         eng.encode(A)
-        eng.decode_begin(prompt, A, 1, opts)
+        eng.decode_begin(prompt, A, G, opts)
         eng.decode_run(3 + steps)
         torch.cuda.synchronize()
     if os.environ.get("BW_TIME"):
@@ -87,14 +93,17 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             print(f"{name}: {e0.elapsed_time(e1) / 5:.3f} ms")
-        eng.decode_begin(prompt, A, 1, opts)
+        eng.decode_begin(prompt, A, G, opts)
         eng.decode_run(3)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         eng.decode_run(128)
         e1.record()
         torch.cuda.synchronize()
-        print(f"decode step: {e0.elapsed_time(e1) / 128 * 1000:.1f} us")
+        us = e0.elapsed_time(e1) / 128 * 1000
+        d, L, V, ffn = dims.d_model, dims.dec_layers, dims.vocab, dims.ffn
+        gb = (2.0 * (L * (6 * d * d + 2 * d * ffn) + V * d) + A * 2.0 * L * 2 * eng.S * d + A * G * 2.0 * L * 2 * 68 * d) / 1e9
+        print(f"decode step (A={A} G={G} S={eng.S}): {us:.1f} us, {A * 1e6 / us:.0f} tok/s, algorithmic {gb:.2f} GB/step -> {gb / us * 1e6:.0f} GB/s")
     toks, fin, pos = eng.decode_read()
     print("pos", pos, "tokens", toks[0, :12].tolist())
 
