@@ -10,6 +10,7 @@
 #   ncu_encoder  ncu --set full of log-mel / tcgen05 GEMM / tcgen05 attention / LayerNorm
 #   configs      tools/bench_configs.py C3 C5 C4 (BASELINE.json configs bench.py does not time)
 #   ncu_batched  launch list + ncu --set full of the batched decoder step (A = 64)
+#   steptime     CUDA-event time of one decoder step at several (audios, beams, chunk length) shapes
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD TRANSFORMERS_OFFLINE=1 HF_HUB_OFFLINE=1 TOKENIZERS_PARALLELISM=false
@@ -23,8 +24,17 @@ for sec in "$@"; do
   echo "=================== section $sec ($(date +%H:%M:%S))"
   case $sec in
   tests)
-    timeout 2400 python -m pytest tests -q -p no:cacheprovider -m gpu -s --durations=15 ${PYTEST_ARGS} > ${O}_tests_full.log 2>&1
-    grep -E "^\[|passed|failed|error|FAILED|ERROR" ${O}_tests_full.log | tail -60 | tee ${O}_tests.log ;;
+    # one pytest process per file: a trapped kernel poisons only its own process.  The CTA-pair GEMM goes first; if it fails the
+    # rest of the call runs the encoder on the first-generation kernel (BW_GEMM2=0) so one bug does not cost the whole call
+    timeout 900 python -m pytest tests/test_ops_gpu.py -q -p no:cacheprovider -m gpu -k "pair" --tb=short > ${O}_tests_pair.log 2>&1
+    tail -3 ${O}_tests_pair.log
+    if ! grep -q " passed" ${O}_tests_pair.log || grep -q "failed\|error" ${O}_tests_pair.log; then export BW_GEMM2=0; echo "!! gemm_tc2 failed: BW_GEMM2=0 for the rest"; fi
+    : > ${O}_tests.log
+    for f in tests/test_ops_gpu.py tests/test_model_gpu.py tests/test_pipeline_gpu.py tests/test_large_gpu.py; do
+      n=$(basename $f .py)
+      timeout 1500 python -m pytest $f -q -p no:cacheprovider -m gpu -s --durations=8 --tb=short ${PYTEST_ARGS} > ${O}_${n}_full.log 2>&1
+      grep -E "^\[|passed|failed|FAILED|ERROR|Error" ${O}_${n}_full.log | tail -40 | tee -a ${O}_tests.log
+    done ;;
   bench)
     timeout 900 python bench.py --steps 10 --warmup 3 2> ${O}_bench.err | tee ${O}_bench.json | cut -c1-1500
     tail -2 ${O}_bench.err | cut -c1-300
@@ -56,11 +66,17 @@ for sec in "$@"; do
     BW_A=${BW_A:-64} BW_STEPS=2 BW_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_batched_launches.csv \
       python tools/profile_decode.py > ${O}_ncu_batched_list.log 2>&1
     tail -1 ${O}_ncu_batched_list.log; python tools/ncu_summary.py --launch-list ${O}_batched_launches.csv | tee ${O}_batched_launches_summary.txt | head -40
-    for spec in ${BATCHED_KERNELS:-"cross_attn:40:2" "gemv_kernel:300:3"}; do
+    for spec in ${BATCHED_KERNELS:-"cross_attn:40:2" "gemm_tc_kernel:10:8" "gemm_tc2:20:6" "resid_ln:100:2" "self_attn:40:2"}; do
       IFS=: read -r pat skip cnt <<< "$spec"
       BW_A=${BW_A:-64} BW_STEPS=2 BW_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c $cnt \
         -o ${O}_b_$pat python tools/profile_decode.py > ${O}_ncu_b_$pat.log 2>&1
       tail -1 ${O}_ncu_b_$pat.log; summ ${O}_b_$pat.ncu-rep | tee ${O}_b_${pat}_summary.txt
+    done ;;
+  steptime)
+    # CUDA-event time of one decoder step at several batch shapes (+ algorithmic GB/s), encoder and log-mel times
+    for spec in ${STEP_SPECS:-"1:1:30" "64:1:30" "32:1:15" "64:5:30" "8:1:30"}; do
+      IFS=: read -r a g c <<< "$spec"
+      BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 600 python tools/profile_decode.py 2>&1 | grep -E "decode step|encode|logmel|Error|error" | tee -a ${O}_steptime.log
     done ;;
   *) echo "unknown section $sec" ;;
   esac
