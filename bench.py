@@ -299,6 +299,8 @@ def main():
     n_words = [len(o["text"].split()) for o in outs]
     assert len(outs) == A and min(n_words) >= 1, n_words
 
+    # ---- the other BASELINE.json configurations (C3 / C5 / C4), every rank its own shard, same public API with host buffers
+    configs = extra_configs(model, weights, dev, rank, world, dist) if os.environ.get("BW_BENCH_CONFIGS", "C3,C5,C4") not in ("", "0") else {}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -333,6 +335,7 @@ def main():
                      "traffic_source": traffic_src,
                      "bytes_per_step": bytes_step, "ms_per_decoder_step": step_ms},
     }
+    line["configs"] = configs
     if not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline()
@@ -345,6 +348,51 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_configs(model, weights, dev, rank, world, dist):
+    """BASELINE.json configs[2..4] beside the headline: C3 (64 x 30 s, greedy + word timestamps), C5 (64 x 30 s, beam 5) and C4
+    (32 streams, 15 s window) PER GPU -- at N GPUs the job is N x that (64 x 8 = 512 chunks, 32 x 8 = 256 streams: the sizes
+    BASELINE.json quotes).  Whole-job value = units of all ranks / max-over-ranks time; each entry carries its own decoder-step roofline."""
+    import torch
+
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.engine import interpolate_positions
+    from tools.bench_configs import run_batch, run_streaming
+
+    want = [c for c in os.environ.get("BW_BENCH_CONFIGS", "C3,C5,C4").split(",") if c]
+    out = {}
+
+    def agg(key_s):
+        t = torch.tensor([key_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for c in want:
+        try:
+            if c in ("C3", "C5"):
+                beams, wts = (1, True) if c == "C3" else (5, False)
+                model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True, suppress_timestamps=not wts)
+                r = run_batch(c, 64, beams, wts, NEW_TOKENS, 2, PRESET, False, model=model, weights=weights, device=str(dev))
+                dt = agg(r["seconds_per_batch"])
+                r.update({"n_gpus": world, "chunks_total": 64 * world, "seconds_per_batch_max_over_ranks": dt,
+                          "tokens_per_sec": 64 * world * NEW_TOKENS / dt, "rtfx": 64 * world * CHUNK_S / dt})
+            elif c == "C4":
+                model.generation_config = S.make_generation_config(PRESET, eos_suppressed=True, suppress_timestamps=False)
+                w15 = dict(weights)
+                w15["enc.pos"] = interpolate_positions(weights["enc.pos"], 15).to(dev)
+                r = run_streaming(32, 24, PRESET, False, model=model, weights15=w15, device=str(dev))
+                tick = agg(r["median_tick_s"])
+                r.update({"n_gpus": world, "streams_total": 32 * world, "median_tick_s_max_over_ranks": tick,
+                          "realtime_streams_sustained": 32 * world * 0.5 / tick})
+            else:
+                continue
+            out[c] = r
+        except Exception as ex:  # a config that fails must not take the headline down with it
+            out[c] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline():

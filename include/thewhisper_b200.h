@@ -133,6 +133,12 @@ int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, co
  * memory, rows beyond read as zero (tied LM head).  force_bn: 0 auto, 32 (decoder tile), 64, 128, 256. */
 int bw_op_gemm_splitk(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t n_valid, int32_t ksplit, int32_t force_bn,
                       float* out_partials, int32_t* ksplit_used, void* stream);
+/* The decoder-step projection (gemm_dec.cu): weights as the 128-row MMA operand, Q activation rows as the N operand, K split over
+ * CTAs.  Writes the raw fp32 partial sums [*ksplit_used][Q][N] (want_split = 0: one split); W has n_valid (<= N) rows in memory. */
+int bw_op_gemm_dec(const void* X, const void* W, int32_t Q, int32_t N, int32_t K, int32_t n_valid, int32_t want_split, float* out_partials,
+                   int32_t* ksplit_used, void* stream);
+/* h[q, n] = bf16(GELU(sum_s partials[s][q][n] + bias[n])) */
+int bw_op_gelu_bias(const float* partials, int32_t nsplit, const float* bias, void* h_bf16, int32_t Q, int32_t N, void* stream);
 /* x[q] += bias + sum_s partials[s][q] (s ascending: deterministic), y[q] = LayerNorm(x[q]) as bf16 (y may be NULL). */
 int bw_op_resid_ln(float* x, const float* partials, int32_t nsplit, const float* bias, const float* ln_g, const float* ln_b, void* y_bf16,
                    int32_t Q, int32_t D, void* stream);

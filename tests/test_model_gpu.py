@@ -128,7 +128,7 @@ def test_encoder_parity(cuda, tag, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("tag", ["tiny10", "small30"])
-@pytest.mark.parametrize("path", ["mega", "perop", "batched"])
+@pytest.mark.parametrize("path", ["mega", "perop", "batched", "batched-xstream"])
 def test_teacher_forced_logits_and_greedy(cuda, tag, path, monkeypatch):
     """path: the persistent one-kernel decoder step (default), the per-op GEMV kernels (BW_NO_MEGA=1; beams / timestamp rules
     on one or two sequences) or the batched tensor-core step (what >= 3 sequences run; forced here for one sequence)."""
@@ -137,8 +137,10 @@ def test_teacher_forced_logits_and_greedy(cuda, tag, path, monkeypatch):
 
     if path != "mega":
         monkeypatch.setenv("BW_NO_MEGA", "1")
-    if path == "batched":
+    if path.startswith("batched"):
         monkeypatch.setenv("BW_BATCH_MIN", "1")
+    if path == "batched-xstream":
+        monkeypatch.setenv("BW_XATTN_STREAM_MIN", "1")
     meta, gold, model = _model_case(tag)
     chunk = meta["chunk_s"]
     eng = _engine(model, chunk, max_audios=1)
@@ -190,7 +192,7 @@ def test_teacher_forced_logits_and_greedy(cuda, tag, path, monkeypatch):
         assert gen.tolist() == g[: len(gen)].tolist()
 
 
-@pytest.mark.parametrize("path", ["mega", "perop", "batched"])
+@pytest.mark.parametrize("path", ["mega", "perop", "batched", "batched-xstream"])
 def test_batch_rows_agree(cuda, path, monkeypatch):
     """B=3 audios decoded together give the tokens of the B=1 runs.  mega: B=1 on the persistent kernel, B=3 on the per-op GEMV
     kernels (same fp32 activations); perop: both on the GEMV kernels; batched: both on the tensor-core step (a row of the MMA tile
@@ -200,9 +202,11 @@ def test_batch_rows_agree(cuda, path, monkeypatch):
 
     if path == "perop":
         monkeypatch.setenv("BW_NO_MEGA", "1")
-    if path == "batched":
+    if path.startswith("batched"):
         monkeypatch.setenv("BW_NO_MEGA", "1")
         monkeypatch.setenv("BW_BATCH_MIN", "1")
+        if path == "batched-xstream":  # the large-batch cross-attention kernel (one CTA per (audio, head), online softmax)
+            monkeypatch.setenv("BW_XATTN_STREAM_MIN", "1")
     else:
         monkeypatch.setenv("BW_BATCH_MIN", "1000")
 

@@ -25,7 +25,20 @@ def _worker(rank, world, port, q):
     if rank == 0:
         g = torch.Generator().manual_seed(0)
         w = {"enc.0.wqkv": torch.randn(12, 4, generator=g).to(torch.bfloat16), "enc.0.bqkv": torch.randn(12, generator=g)}
+    import torch.distributed.distributed_c10d as c10d
+
+    calls = {"n": 0}
+    orig = c10d.broadcast
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+
+    dist.broadcast = counting
     w = broadcast_weights(w, torch.device("cpu"))
+    dist.broadcast = orig
+    assert calls["n"] == 1, calls  # ONE tensor collective for all weights
+    assert w["enc.0.wqkv"].dtype == torch.bfloat16 and tuple(w["enc.0.wqkv"].shape) == (12, 4)
     mine = list(shard_range(7, rank, world))
     local = [(i, float(w["enc.0.bqkv"].sum()) + i) for i in mine]
     allr = gather_results(local)

@@ -64,6 +64,8 @@ SYMBOLS = {
     "bw_host_merge_overlapping": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
     "bw_op_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _I, _I, _I, _P]),
     "bw_op_gemm_splitk": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
+    "bw_op_gemm_dec": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
+    "bw_op_gelu_bias": (C.c_int, [_P, _I, _P, _P, _I, _I, _P]),
     "bw_op_resid_ln": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bw_op_attn_enc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "bw_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),

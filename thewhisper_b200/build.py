@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libthewhisper_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "attn_enc.cu", "logmel.cu", "decode.cu", "decode_stream.cu", "decode_mega.cu", "timestamps.cu", "hostproc.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_dec.cu", "attn_enc.cu", "logmel.cu", "decode.cu", "decode_stream.cu", "decode_mega.cu", "timestamps.cu", "hostproc.cu"]
 HEADERS = ["common.cuh", "kernels.h", "decode.cuh", "decode_mega_common.cuh", os.path.join("..", "..", "include", "thewhisper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -224,13 +224,14 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
   return 0;
 }
 
-constexpr int BSPLIT = 4;  // split-K of the batched step's residual GEMMs (out-proj, cross out-proj, fc2)
+constexpr int DPART_PER_ROW = 20480;  // floats of split-K partial sums per sequence: ksplit * N <= (SMs / n_tiles) * (n_tiles * 128) < 20480
 
-// One decoder step for Q >= 3 sequences on the tensor cores: every projection is a tcgen05 GEMM over the [Q, K] activations
-// (gemm_tc_kernel<32>: 32-column weight tiles so N / 32 CTAs stream the weight matrix once, 8-stage TMA ring), LayerNorm + residual
-// update fused in one small kernel between them, the attention kernels of the per-op path with bf16 outputs.  11 launches per
-// layer in one CUDA graph; weights are read once per step whatever Q is (the GEMV path re-reads L2 per 8 rows and runs
-// 2*Q*params flops on the fp32 pipes: compute-bound from Q ~ 16).
+// One decoder step for Q >= 3 sequences on the tensor cores.  Every projection is a weight-streaming tcgen05 GEMM (gemm_dec.cu:
+// weights = 128-row MMA operand, activations = N operand, K split so that a launch is one DRAM round trip) that leaves raw split-K
+// partial sums; the kernel that consumes them adds them in a fixed order together with bias / scale / activation:
+//   resid_ln (residual update + LayerNorm), the attention kernels (q / k / v), gelu_bias (fc1 -> fc2 operand).
+// 12 launches per layer in one CUDA graph, chained by programmatic dependent launch; weights are read once per step whatever Q is
+// (the GEMV path runs 2*Q*params flops on the fp32 pipes: 46 ms per step at Q = 64, profiles/r2a_summary.md).
 int step_batched_impl(bw_engine* e, cudaStream_t st);
 int step_batched(bw_engine* e, cudaStream_t st) {
   // programmatic dependent launch for every kernel of the step (BW_PDL=0: plain stream order)
@@ -247,17 +248,14 @@ int step_batched_impl(bw_engine* e, cudaStream_t st) {
   const int D = e->D, H = e->H, S = e->S, ffn = e->cfg.ffn, Tmax = e->Tmax, Q = e->Q, A = e->A, G = e->G;
   const long long self_layer = (long long)e->cfg.max_audios * e->cfg.max_beams * Tmax * D;
   const long long cross_layer = (long long)e->cfg.max_audios * H * S * 64;
-  const long long pstride = (long long)e->cfg.max_audios * e->cfg.max_beams * D;
-  auto proj = [&](const bf16* in, int K, const bf16* W, int N, const float* bias, float alpha, int act, float* of32, bf16* obf) {
-    GemmEpi ep = plainEpi(Q, N);
-    ep.bias = bias; ep.alpha = alpha; ep.act = act; ep.out_f32 = of32; ep.out_bf16 = obf;
-    return gemm_tc_split(st, plainA(in, Q, K), W, 1, Q, N, K, ep, 32, 1, 0);
-  };
-  auto proj_split = [&](const bf16* in, int K, const bf16* W, int N, int* used) {
-    GemmEpi ep = plainEpi(Q, N);
-    ep.out_f32 = e->dpart;
-    *used = gemm_tc_ksplit(K, BSPLIT);
-    return gemm_tc_split(st, plainA(in, Q, K), W, 1, Q, N, K, ep, 32, BSPLIT, pstride);
+  // raw partial sums of out[Q, N] = in[Q, K] W[N, K]^T into dpart ([split][Q][N]); returns the split count
+  auto proj = [&](const bf16* in, int K, const bf16* W, int N, int* ns) {
+    const DecGemmPlan pl = gemm_dec_plan(Q, N, K, e->num_sms, true);
+    BW_CHECK((long long)pl.ksplit * N <= DPART_PER_ROW, "batched step: %d splits x N=%d exceed the partial-sum buffer", pl.ksplit, N);
+    GemmEpi ep;
+    ep.out_f32 = e->dpart; ep.row_stride = N;
+    *ns = pl.ksplit;
+    return gemm_dec(st, in, W, Q, N, K, 0, ep, pl, (long long)Q * N);
   };
   if (int rc = launch_embed(st, e->embed, e->dec_pos, e->tokens, e->pos, e->dx, Q, D, Tmax)) return rc;
   int ns = 0;                  // partial sums of the previous residual GEMM still to be folded into dx
@@ -267,26 +265,22 @@ int step_batched_impl(bw_engine* e, cudaStream_t st) {
     bf16* kc = e->self_k + l * self_layer;
     bf16* vc = e->self_v + l * self_layer;
     // dx += fc2 partials of layer l-1 (+ b2); LN1 -> dbn
-    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, pbias, L.ln1g, L.ln1b, e->dbn, Q, D)) return rc;
-    // fused QKV projection (q scaled by dh^-1/2; k has no bias: bqkv holds zeros there), fp32 [Q, 3D]
-    {
-      GemmEpi ep = plainEpi(Q, 3 * D);
-      ep.bias = L.bqkv; ep.out_f32 = e->dqkv;
-      ep.alpha = 0.125f; ep.alpha_cols = D;
-      if (int rc = gemm_tc_split(st, plainA(e->dbn, Q, D), L.wqkv, 1, Q, 3 * D, D, ep, 32, 1, 0)) return rc;
-    }
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, (long long)Q * D, pbias, L.ln1g, L.ln1b, e->dbn, Q, D)) return rc;
+    if (int rc = proj(e->dbn, D, L.wqkv, 3 * D, &ns)) return rc;
     {
       SelfAttnArgs s;
-      s.qkv = e->dqkv; s.kc = kc; s.vc = vc; s.kc_w = kc; s.vc_w = vc; s.anc = e->use_anc ? e->anc : nullptr; s.out_bf16 = e->dba; s.pos = e->pos;
+      s.qkv = e->dpart; s.nsplit = ns; s.split_stride = (long long)Q * 3 * D; s.qkv_bias = L.bqkv; s.q_alpha = 0.125f;
+      s.kc = kc; s.vc = vc; s.kc_w = kc; s.vc_w = vc; s.anc = e->use_anc ? e->anc : nullptr; s.out_bf16 = e->dba; s.pos = e->pos;
       s.H = H; s.D = D; s.Tmax = Tmax;
       if (int rc = launch_self_attn(st, s, Q)) return rc;
     }
-    if (int rc = proj_split(e->dba, D, L.wo, D, &ns)) return rc;
-    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, L.bo, L.ln2g, L.ln2b, e->dbn, Q, D)) return rc;
-    if (int rc = proj(e->dbn, D, L.xwq, D, L.xbq, 0.125f, 0, e->dq, nullptr)) return rc;
+    if (int rc = proj(e->dba, D, L.wo, D, &ns)) return rc;
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, (long long)Q * D, L.bo, L.ln2g, L.ln2b, e->dbn, Q, D)) return rc;
+    if (int rc = proj(e->dbn, D, L.xwq, D, &ns)) return rc;
     {
       CrossAttnArgs c;
-      c.q = e->dq; c.kc = e->cross_k + l * cross_layer; c.vc = e->cross_v + l * cross_layer; c.out_bf16 = e->dba;
+      c.q = e->dpart; c.nsplit = ns; c.split_stride = (long long)Q * D; c.q_bias = L.xbq; c.q_alpha = 0.125f;
+      c.kc = e->cross_k + l * cross_layer; c.vc = e->cross_v + l * cross_layer; c.out_bf16 = e->dba;
       c.part_o = e->part_o; c.part_ml = e->part_ml; c.counters = e->xcounters;
       c.S = S; c.H = H; c.D = D; c.G = G; c.pos = e->pos;
       if (e->opts.record_alignment && e->cfg.n_align_heads > 0) {
@@ -295,17 +289,19 @@ int step_batched_impl(bw_engine* e, cudaStream_t st) {
       }
       if (int rc = launch_cross_attn(st, c, A)) return rc;
     }
-    if (int rc = proj_split(e->dba, D, L.xwo, D, &ns)) return rc;
-    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, L.xbo, L.ln3g, L.ln3b, e->dbn, Q, D)) return rc;
-    if (int rc = proj(e->dbn, D, L.w1, ffn, L.b1, 1.0f, 1, nullptr, e->dbh)) return rc;
-    if (int rc = proj_split(e->dbh, ffn, L.w2, D, &ns)) return rc;
+    if (int rc = proj(e->dba, D, L.xwo, D, &ns)) return rc;
+    if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, (long long)Q * D, L.xbo, L.ln3g, L.ln3b, e->dbn, Q, D)) return rc;
+    if (int rc = proj(e->dbn, D, L.w1, ffn, &ns)) return rc;
+    if (int rc = launch_gelu_bias(st, e->dpart, ns, (long long)Q * ffn, L.b1, e->dbh, Q, ffn)) return rc;
+    if (int rc = proj(e->dbh, ffn, L.w2, D, &ns)) return rc;
     pbias = L.b2;
   }
-  if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, pstride, pbias, e->dec_lnf_g, e->dec_lnf_b, e->dbn, Q, D)) return rc;
-  {  // tied LM head: N = V rounded up to 32 (rows of the embedding beyond V are zero-filled by TMA, the pad columns receive 0)
-    GemmEpi ep = plainEpi(Q, e->Vp);
-    ep.out_f32 = e->logits; ep.n_valid = e->V;
-    if (int rc = gemm_tc_split(st, plainA(e->dbn, Q, D), e->embed, 1, Q, e->Vp, D, ep, 128, 1, 0)) return rc;
+  if (int rc = launch_resid_ln(st, e->dx, e->dpart, ns, (long long)Q * D, pbias, e->dec_lnf_g, e->dec_lnf_b, e->dbn, Q, D)) return rc;
+  {  // tied LM head: 406 weight tiles, no split; rows of the embedding beyond V are zero-filled by TMA and not stored
+    const DecGemmPlan pl = gemm_dec_plan(Q, e->V, D, e->num_sms, false);
+    GemmEpi ep;
+    ep.out_f32 = e->logits; ep.row_stride = e->Vp;
+    if (int rc = gemm_dec(st, e->dbn, e->embed, Q, e->V, D, e->V, ep, pl, 0)) return rc;
   }
   return 0;
 }
@@ -657,7 +653,7 @@ int bw_engine_finalize(bw_engine* e) {
     if (dalloc(e, "dbn", &e->dbn, qpad * D)) return -1;
     if (dalloc(e, "dba", &e->dba, qpad * D)) return -1;
     if (dalloc(e, "dbh", &e->dbh, qpad * c.ffn)) return -1;
-    if (dalloc(e, "dpart", &e->dpart, (size_t)BSPLIT * Qm * D)) return -1;
+    if (dalloc(e, "dpart", &e->dpart, (size_t)Qm * DPART_PER_ROW)) return -1;
   }
   if (dalloc(e, "lse", &e->lse, (size_t)Qm)) return -1;
   if (dalloc(e, "run_scores", &e->run_scores, (size_t)Qm)) return -1;
@@ -911,6 +907,23 @@ int bw_op_gemm_splitk(const void* A, const void* W, int32_t M, int32_t N, int32_
   *ksplit_used = gemm_tc_ksplit(K, ksplit);
   return gemm_tc_split(static_cast<cudaStream_t>(stream), plainA(static_cast<const bf16*>(A), M, K), static_cast<const bf16*>(W), 1, M, N, K, ep,
                        force_bn, ksplit, (long long)M * N);
+}
+
+int bw_op_gemm_dec(const void* X, const void* W, int32_t Q, int32_t N, int32_t K, int32_t n_valid, int32_t want_split, float* out_partials,
+                   int32_t* ksplit_used, void* stream) {
+  BW_CHECK(X && W && out_partials && ksplit_used, "bw_op_gemm_dec: null pointer");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const DecGemmPlan pl = gemm_dec_plan(Q, N, K, sms, want_split != 0);
+  *ksplit_used = pl.ksplit;
+  GemmEpi ep;
+  ep.out_f32 = out_partials; ep.row_stride = N;
+  return gemm_dec(static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), static_cast<const bf16*>(W), Q, N, K, n_valid, ep, pl, (long long)Q * N);
+}
+
+int bw_op_gelu_bias(const float* partials, int32_t nsplit, const float* bias, void* h_bf16, int32_t Q, int32_t N, void* stream) {
+  BW_CHECK(partials && bias && h_bf16 && nsplit >= 1, "bw_op_gelu_bias: bad arguments");
+  return launch_gelu_bias(static_cast<cudaStream_t>(stream), partials, nsplit, (long long)Q * N, bias, static_cast<bf16*>(h_bf16), Q, N);
 }
 
 int bw_op_resid_ln(float* x, const float* partials, int32_t nsplit, const float* bias, const float* ln_g, const float* ln_b, void* y_bf16,

@@ -39,6 +39,12 @@ struct SelfAttnArgs {
   // bf16, appends them to the cache at position *pos and attends over them (the GEMV path appends in its own epilogue)
   bf16* kc_w = nullptr;
   bf16* vc_w = nullptr;
+  // batched path, split-K projection: qkv holds nsplit raw partial sums ([split][Q][3D], split_stride apart); the kernel adds them in
+  // order, then the bias (qkv_bias [3D]) and scales q by q_alpha.  nsplit = 0: qkv is final (per-op / ksplit = 1 paths).
+  int nsplit = 0;
+  long long split_stride = 0;
+  const float* qkv_bias = nullptr;
+  float q_alpha = 1.0f;
 };
 
 constexpr int XSPLIT = 12;   // key splits per (audio, head) in cross attention (<= 128 keys each: S <= 1536)
@@ -60,6 +66,11 @@ struct CrossAttnArgs {
   const int* head_slots = nullptr;  // [H] slot per head for this layer or -1
   int Ha = 0, Tcap = 0, step_base = 0;
   const int* pos = nullptr;
+  // batched path, split-K cross-q projection: q holds nsplit raw partial sums ([split][Q][D]); summed in order, + q_bias, * q_alpha
+  int nsplit = 0;
+  long long split_stride = 0;
+  const float* q_bias = nullptr;
+  float q_alpha = 1.0f;
 };
 
 struct SelectArgs {

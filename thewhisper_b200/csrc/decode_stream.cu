@@ -33,6 +33,18 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// value i of a row that may be stored as nsplit raw split-K partial sums (fixed order: deterministic), + bias, * alpha
+__device__ __forceinline__ float split_sum(const float* __restrict__ p, long long idx, int nsplit, long long split_stride,
+                                           const float* __restrict__ bias, int bias_idx, float alpha) {
+  float v = p[idx];
+  if (nsplit > 0) {
+    for (int s = 1; s < nsplit; ++s) v += p[(long long)s * split_stride + idx];
+    if (bias) v += bias[bias_idx];
+    v *= alpha;
+  }
+  return v;
+}
+
 template <int NC, int R>
 struct WRegs {
   uint4 w[R][NC];
@@ -243,22 +255,26 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
     cp_async16(sV + s * 128 + sub * 16, a.vc + off);
   }
   if (a.kc_w && grp == (pos & 15)) {  // the group that reads row `pos` below appends it: k / v of this step, rounded to bf16
-    const float* kp = a.qkv + (long long)q * 3 * a.D + a.D + h * 64 + sub * 8;
-    const float4 k0 = *reinterpret_cast<const float4*>(kp), k1 = *reinterpret_cast<const float4*>(kp + 4);
-    const float4 v0 = *reinterpret_cast<const float4*>(kp + a.D), v1 = *reinterpret_cast<const float4*>(kp + a.D + 4);
+    const long long kidx = (long long)q * 3 * a.D + a.D + h * 64 + sub * 8;
+    float kf[8], vf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      kf[i] = split_sum(a.qkv, kidx + i, a.nsplit, a.split_stride, a.qkv_bias, a.D + h * 64 + sub * 8 + i, 1.0f);
+      vf[i] = split_sum(a.qkv, kidx + a.D + i, a.nsplit, a.split_stride, a.qkv_bias, 2 * a.D + h * 64 + sub * 8 + i, 1.0f);
+    }
     uint4 kw, vw;
-    kw.x = pack_bf16(k0.x, k0.y); kw.y = pack_bf16(k0.z, k0.w); kw.z = pack_bf16(k1.x, k1.y); kw.w = pack_bf16(k1.z, k1.w);
-    vw.x = pack_bf16(v0.x, v0.y); vw.y = pack_bf16(v0.z, v0.w); vw.z = pack_bf16(v1.x, v1.y); vw.w = pack_bf16(v1.z, v1.w);
+    kw.x = pack_bf16(kf[0], kf[1]); kw.y = pack_bf16(kf[2], kf[3]); kw.z = pack_bf16(kf[4], kf[5]); kw.w = pack_bf16(kf[6], kf[7]);
+    vw.x = pack_bf16(vf[0], vf[1]); vw.y = pack_bf16(vf[2], vf[3]); vw.z = pack_bf16(vf[4], vf[5]); vw.w = pack_bf16(vf[6], vf[7]);
     *reinterpret_cast<uint4*>(sK + pos * 128 + sub * 16) = kw;
     *reinterpret_cast<uint4*>(sV + pos * 128 + sub * 16) = vw;
     const long long off = ((long long)q * a.Tmax + pos) * a.D + h * 64 + sub * 8;  // a sequence's newest row lives in its own slot
     *reinterpret_cast<uint4*>(a.kc_w + off) = kw;
     *reinterpret_cast<uint4*>(a.vc_w + off) = vw;
   }
-  const float* qp = a.qkv + (long long)q * 3 * a.D + h * 64 + sub * 8;
   float qv[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) qv[i] = qp[i];
+  for (int i = 0; i < 8; ++i)
+    qv[i] = split_sum(a.qkv, (long long)q * 3 * a.D + h * 64 + sub * 8 + i, a.nsplit, a.split_stride, a.qkv_bias, h * 64 + sub * 8 + i, a.q_alpha);
   cp_async_wait_all();  // each thread reads back only what it copied itself
   float lmax = -INFINITY;
   for (int sb = 0; sb < n; sb += 16) {  // uniform trip count: the shuffles need all 32 lanes
@@ -350,9 +366,9 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
 #pragma unroll
   for (int g = 0; g < GM; ++g) {
     if (g < G) {
-      const float* qp = a.q + (long long)(au * G + g) * a.D + h * 64 + sub * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) qv[g][j] = qp[j];
+      for (int j = 0; j < 8; ++j)
+        qv[g][j] = split_sum(a.q, (long long)(au * G + g) * a.D + h * 64 + sub * 8 + j, a.nsplit, a.split_stride, a.q_bias, h * 64 + sub * 8 + j, a.q_alpha);
     }
   }
   const int slot = a.head_slots ? a.head_slots[h] : -1;
@@ -475,6 +491,179 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
   if (threadIdx.x == 0) a.counters[au * a.H + h] = 0u;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention for large batches: ONE CTA streams all S keys of one (audio, head) through a double-buffered smem ring with an
+// online softmax -- no key splits, so no partial results, no atomics, no __threadfence and no merge pass (the split kernel above
+// spends ~45 % of its issue slots on those and on block reductions at A = 64: profiles/r2a_summary.md, 0.68 of the HBM peak).
+// Chosen when A * H CTAs fill the machine at least twice; small batches keep the split kernel (more CTAs per byte).
+//   QK : thread t owns key t of the 128-key tile: its 128-byte K row sits in smem with the 16-byte pieces XOR-swizzled by (row & 7),
+//        so a row-per-thread LDS.128 is conflict-free; 64 FMAs per beam, no shuffles
+//   PV : thread (t / 16, t % 16) owns 4 of the 64 output dims for every 8th key; the 8 key slices are folded once at the very end
+// One tile (16 KB K + 16 KB V) is in flight per CTA while the previous one is processed; 64 KB smem -> 3 CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int XT = 128;  // keys per tile
+
+template <int GM>
+__global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnArgs a) {
+  extern __shared__ __align__(128) uint8_t dyn[];  // K [2][XT][128 B] | V [2][XT][128 B] | sp [GM][XT] | sq [GM][64] | red [GM][4] | fold [8][GM][64]
+  uint8_t* sK = dyn;
+  uint8_t* sV = dyn + 2 * XT * 128;
+  float* sp = reinterpret_cast<float*>(dyn + 4 * XT * 128);
+  float* sq = sp + GM * XT;
+  float* red = sq + GM * 64;
+  float* fold = red + GM * 4;
+  const int h = blockIdx.x, au = blockIdx.y;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int G = (GM == 1) ? 1 : a.G;
+  const int S = a.S;
+  const int ntiles = (S + XT - 1) / XT;
+  const bf16* kbase = a.kc + ((long long)au * a.H + h) * S * 64;
+  const bf16* vbase = a.vc + ((long long)au * a.H + h) * S * 64;
+
+  auto issue_tile = [&](int tile, int stage) {
+    const int r0 = tile * XT;
+    const int nrows = min(XT, S - r0);
+    uint8_t* dk = sK + stage * XT * 128;
+    uint8_t* dv = sV + stage * XT * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = t + 128 * j;  // 16-byte piece of the tile: row i / 8, piece i % 8 (global: contiguous)
+      const int row = i >> 3, c = i & 7;
+      if (row < nrows) {
+        cp_async16(dk + row * 128 + ((c ^ (row & 7)) << 4), kbase + (long long)(r0 + row) * 64 + c * 8);
+        cp_async16(dv + row * 128 + (c << 4), vbase + (long long)(r0 + row) * 64 + c * 8);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // the encoder K/V are constant during decoding: the first tile is requested before the programmatic-launch wait
+  issue_tile(0, 0);
+  pdl_wait();
+  pdl_launch();
+  for (int i = t; i < G * 64; i += 128)
+    sq[i] = split_sum(a.q, (long long)(au * G + i / 64) * a.D + h * 64 + (i & 63), a.nsplit, a.split_stride, a.q_bias, h * 64 + (i & 63), a.q_alpha);
+  const int slot = a.head_slots ? a.head_slots[h] : -1;
+  float* align_base = nullptr;
+  if (slot >= 0 && a.align) {
+    const int step = *a.pos - a.step_base;
+    if (step >= 0 && step < a.Tcap) align_base = a.align + (((long long)au * a.Ha + slot) * a.Tcap + step) * S;
+  }
+  float m_run[GM], l_part[GM], o[GM][4];
+#pragma unroll
+  for (int g = 0; g < GM; ++g) {
+    m_run[g] = -INFINITY;
+    l_part[g] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) o[g][d] = 0.f;
+  }
+  const int kg = t >> 4, dg = t & 15;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = tile & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile landed for everybody; everybody is done with the other stage, sp and red of the previous tile
+    if (tile + 1 < ntiles) issue_tile(tile + 1, stage ^ 1);
+    const int r0 = tile * XT;
+    const bool valid = r0 + t < S;
+    // ---- scores of key t for every beam
+    float sc[GM];
+#pragma unroll
+    for (int g = 0; g < GM; ++g) sc[g] = 0.f;
+    {
+      const uint8_t* krow = sK + stage * XT * 128 + t * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float kf[8];
+        unpack8(*reinterpret_cast<const uint4*>(krow + ((c ^ (t & 7)) << 4)), kf);
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+          if (g < G) {
+            const float4 q0 = *reinterpret_cast<const float4*>(sq + g * 64 + c * 8);
+            const float4 q1 = *reinterpret_cast<const float4*>(sq + g * 64 + c * 8 + 4);
+            float s0 = sc[g];
+            s0 = fmaf(q0.x, kf[0], s0); s0 = fmaf(q0.y, kf[1], s0); s0 = fmaf(q0.z, kf[2], s0); s0 = fmaf(q0.w, kf[3], s0);
+            s0 = fmaf(q1.x, kf[4], s0); s0 = fmaf(q1.y, kf[5], s0); s0 = fmaf(q1.z, kf[6], s0); s0 = fmaf(q1.w, kf[7], s0);
+            sc[g] = s0;
+          }
+        }
+      }
+    }
+    if (align_base && valid) align_base[r0 + t] = sc[0];
+#pragma unroll
+    for (int g = 0; g < GM; ++g) {
+      if (g < G) {
+        const float v = warp_max(valid ? sc[g] : -INFINITY);
+        if (lane == 0) red[g * 4 + warp] = v;
+      }
+    }
+    __syncthreads();
+    float scale[GM];
+#pragma unroll
+    for (int g = 0; g < GM; ++g) {
+      scale[g] = 1.f;
+      if (g < G) {
+        const float mt = fmaxf(fmaxf(red[g * 4], red[g * 4 + 1]), fmaxf(red[g * 4 + 2], red[g * 4 + 3]));
+        const float m_new = fmaxf(m_run[g], mt);  // finite: every tile holds at least one valid key
+        scale[g] = __expf(m_run[g] - m_new);      // first tile: exp(-inf) = 0
+        const float p = valid ? __expf(sc[g] - m_new) : 0.f;
+        l_part[g] = l_part[g] * scale[g] + p;
+        sp[g * XT + t] = p;
+        m_run[g] = m_new;
+      }
+    }
+    __syncthreads();
+    // ---- P.V: this thread's 4 dims over keys kg, kg + 8, ...
+    {
+      const uint8_t* vt = sV + stage * XT * 128 + dg * 8;
+#pragma unroll
+      for (int g = 0; g < GM; ++g)
+        if (g < G) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) o[g][d] *= scale[g];
+        }
+#pragma unroll 4
+      for (int j = 0; j < XT / 8; ++j) {
+        const int k = kg + 8 * j;
+        const uint2 vv = *reinterpret_cast<const uint2*>(vt + k * 128);
+        const float2 v01 = unpack_bf16(vv.x), v23 = unpack_bf16(vv.y);
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+          if (g < G) {
+            const float p = sp[g * XT + k];  // 0 for the rows beyond S (their V bytes are stale smem: multiplied by 0 ... but NaN-safe?)
+            if (p != 0.f) {
+              o[g][0] = fmaf(p, v01.x, o[g][0]); o[g][1] = fmaf(p, v01.y, o[g][1]);
+              o[g][2] = fmaf(p, v23.x, o[g][2]); o[g][3] = fmaf(p, v23.y, o[g][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- fold: sum of exp over the 128 key owners, outputs over the 8 key slices
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < GM; ++g) {
+    if (g < G) {
+      const float v = warp_sum(l_part[g]);
+      if (lane == 0) red[g * 4 + warp] = v;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) fold[(kg * GM + g) * 64 + dg * 4 + d] = o[g][d];
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < G * 64; i += 128) {
+    const int g = i >> 6, d = i & 63;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += fold[(j * GM + g) * 64 + d];
+    const float l = (red[g * 4] + red[g * 4 + 1]) + (red[g * 4 + 2] + red[g * 4 + 3]);
+    const float r = acc / l;
+    const long long off = (long long)(au * G + g) * a.D + h * 64 + d;
+    if (a.out_bf16) a.out_bf16[off] = __float2bfloat16(r);
+    else a.out[off] = r;
+  }
+}
+
 template <int MB, int NC, int R, bool PIPE>
 int launch_gemv_t(cudaStream_t st, const GemvArgs& a, int grid, int rpw, size_t smem) {
   static bool attr = false;
@@ -537,6 +726,23 @@ int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A) {
   if (!attr) {
     BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemG));
     attr = true;
+  }
+  {  // large batches: one CTA per (audio, head) streams all keys (no splits / partials / merge)
+    // CTAs (A * H) from which the streaming kernel is used; 0 = never.  (Read per launch: launches happen at graph capture only.)
+    const char* ev = getenv("BW_XATTN_STREAM_MIN");
+    const int stream_min = ev ? atoi(ev) : 296;
+    if (stream_min > 0 && A * a.H >= stream_min) {
+      auto smem_of = [](int gm) { return (size_t)4 * XT * 128 + (size_t)(gm * XT + gm * 64 + gm * 4 + 8 * gm * 64) * sizeof(float); };
+      static bool attr2 = false;
+      if (!attr2) {
+        BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(1)));
+        BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_stream_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(MAXG)));
+        attr2 = true;
+      }
+      if (a.G == 1) BW_CUDA_OK(launch_k(cross_attn_stream_kernel<1>, dim3(a.H, A), dim3(128), smem_of(1), st, a));
+      else BW_CUDA_OK(launch_k(cross_attn_stream_kernel<MAXG>, dim3(a.H, A), dim3(128), smem_of(MAXG), st, a));
+      return 0;
+    }
   }
   if (a.G == 1) BW_CUDA_OK(launch_k(cross_attn_kernel<1>, dim3(XSPLIT, a.H, A), dim3(128), smem1, st, a));
   else BW_CUDA_OK(launch_k(cross_attn_kernel<MAXG>, dim3(XSPLIT, a.H, A), dim3(128), smemG, st, a));

@@ -7,7 +7,9 @@
 // accumulator serialises epilogue and main loop inside a CTA.  Here
 //   * a CTA PAIR owns a 256 x BN tile: each CTA stages its own 128 rows of A and HALF of the W tile (BN / 2 rows); the leader's
 //     tcgen05.mma.cta_group::2 reads both halves, so per SM and k-block 32 KB feed 128 x 256 x 64 MACs (64 B/clk/SM at BN = 256);
-//   * CTAs are persistent (one pair per two SMs) and walk tiles m-fastest, so the pairs running together share one W tile in L2;
+//   * CTAs are persistent (one pair per two SMs) and walk tiles n-fastest: the pairs running together work on a few 256-row bands of
+//     A against ALL of W (<= 13 MB: L2-resident), so A streams from DRAM once (m-fastest re-read the 245 MB A of a 64-chunk batch once
+//     per W tile: 3.7 GB of DRAM reads for one fc1, profiles/r2b_summary.md);
 //   * accumulators are double-buffered in TMEM (2 x BN columns): the epilogue of tile i (bias / GELU / residual / bf16 pack, four
 //     warps per CTA) runs under the main loop of tile i + 1.
 // Barrier protocol (CUTLASS sm100 2-SM pipeline, restated in raw PTX): TMA loads of BOTH CTAs complete on the LEADER's full[s]
@@ -134,7 +136,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int it = 0;
       for (int tile = pair; tile < ntiles; tile += npairs) {
-        const int m2 = tile % p.tiles_m2, nt = tile / p.tiles_m2;
+        const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
         const int row0 = m2 * 2 * BM + (int)rank * BM;
         const int wrow0 = nt * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -177,7 +179,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const GemmEpi& e = p.epi;
     int at = 0;
     for (int tile = pair; tile < ntiles; tile += npairs, ++at) {
-      const int m2 = tile % p.tiles_m2, nt = tile / p.tiles_m2;
+      const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
       const int as = at & 1;
       const uint32_t aph = (at >> 1) & 1;
       mbar_wait(&accum_full[as], aph);

@@ -55,6 +55,21 @@ int gemm_tc2(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, int K,
 int gemm_simt(cudaStream_t st, const GemmA& a, const bf16* W, int B, int rows, int N, int K, const GemmEpi& epi);
 
 // ---------------------------------------------------------------------------------------------
+// decoder-step projections (gemm_dec.cu): weights are the 128-row MMA operand, the Q activation rows the N operand, K split
+// across CTAs so that one launch is one DRAM round trip.  ksplit > 1: raw fp32 partial sums at out_f32 + z * split_stride
+// ([split][q][n], row pitch epi.row_stride); ksplit == 1: bias / alpha (columns < alpha_cols) / GELU applied, fp32 or bf16 out.
+// ---------------------------------------------------------------------------------------------
+struct DecGemmPlan {
+  int QB = 16, q_tiles = 1, stages = 2, kper = 1, ksplit = 1;
+  size_t smem = 0;
+};
+DecGemmPlan gemm_dec_plan(int Q, int N, int K, int num_sms, bool want_split);
+int gemm_dec(cudaStream_t st, const bf16* X, const bf16* W, int Q, int N, int K, int n_valid, const GemmEpi& epi, const DecGemmPlan& pl,
+             long long split_stride);
+// h[q, n] = bf16(GELU(sum_s part[s][q][n] + bias[n]))
+int launch_gelu_bias(cudaStream_t st, const float* part, int nsplit, long long split_stride, const float* bias, bf16* h, int Q, int N);
+
+// ---------------------------------------------------------------------------------------------
 // encoder attention (non-causal).  qkv: [B*S, 3*D] bf16 (q pre-scaled by dh^-1/2), vt: [B, H, 64, Spad] bf16
 // (zero beyond S), out: [B*S, D] bf16.  head_dim is 64 for every Whisper size.
 // ---------------------------------------------------------------------------------------------
