@@ -109,12 +109,12 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
                         void* stream);
 /* word timestamps for audio a: n_tokens generated tokens starting at alignment row 0, num_frames valid encoder
  * frames (<= S); out_host [n_tokens + 1] seconds */
-int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision,
+int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, double time_precision,
                        float* out_host, void* stream);
 /* the same for n audios in one pass (4 kernel launches + one D2H whatever n is): audio[i], n_tokens[i], num_frames[i];
  * out_host [n][out_pitch] floats, out_pitch >= max n_tokens + 1 */
 int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
-                             float time_precision, float* out_host, int32_t out_pitch, void* stream);
+                             double time_precision, float* out_host, int32_t out_pitch, void* stream);
 
 /* ---- host-side post-processing (no CUDA) ---------------------------------------------------------------------- */
 /* Seam merge of overlapping chunks: the reference's patched `_find_longest_common_sequence`

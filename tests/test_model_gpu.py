@@ -224,3 +224,76 @@ def test_batch_rows_agree(cuda, path, monkeypatch):
         eng.encode(1)
         gen1, _, _ = eng.greedy(prompt[:1], 1, opts, max_new_tokens=16)
         assert gen1[0].tolist() == gen3[i].tolist(), i
+
+
+@pytest.mark.parametrize("ts", [False, True], ids=["plain", "timestamps"])
+@pytest.mark.parametrize("path", ["perop", "batched"])
+def test_beam_candidates_match_transformers(cuda, ts, path, monkeypatch):
+    """Beam search on the device (a12): every decoder step the engine returns, per sequence, its 2G best
+    continuations as (running score + processed log-prob, token).  Checked against transformers itself: log_softmax of the ENGINE's
+    own logits -> SuppressTokensAtBegin / SuppressTokens / WhisperTimeStamp processors (TF generation/logits_process.py:1812-2043,
+    applied after the log-softmax as GenerationMixin._beam_search does, TF generation/utils.py:3254-3257) -> + running score -> topk.
+    Token ids must be identical, scores within 1e-3; over several steps with real reordering in between (block-table permutation)."""
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    monkeypatch.setenv("BW_BATCH_MIN", "1" if path == "batched" else "1000")
+    meta, gold, model = _model_case("tiny10")
+    A, G = 2, 5
+    eng = _engine(model, 10, max_audios=A, max_beams=G)
+    fe = S.make_feature_extractor(10)
+    mels = np.stack([hf_ref.logmel(fe, S.synth_audio(10, seed=s)) for s in (1000, 1001)])
+    eng.set_mel(torch.from_numpy(mels))
+    eng.encode(A)
+    g = model.generation_config
+    opts = _opts(model, ts=ts)
+    prompt = [S.SOT, S.LANG_EN, S.TRANSCRIBE] + ([] if ts else [S.NOTIMESTAMPS])
+    plen = len(prompt)
+    procs = [SuppressTokensAtBeginLogitsProcessor(g.begin_suppress_tokens, begin_index=plen), SuppressTokensLogitsProcessor(g.suppress_tokens)]
+    if ts:
+        procs.append(WhisperTimeStampLogitsProcessor(g, begin_index=plen))
+    Q = A * G
+    eng.decode_begin(np.array([prompt] * Q, dtype=np.int32), A, G, opts)
+    eng.decode_run(plen - 1)
+    seqs = [list(prompt) for _ in range(Q)]
+    run = np.zeros((A, G), dtype=np.float32)
+    run[:, 1:] = -1.0e9
+    rng = np.random.RandomState(3)
+    checked = 0
+    for step in range(6):
+        cs, ct = eng.decode_beam_step(run.reshape(-1))
+        lg = eng.logits().float().cpu()
+        logp = torch.log_softmax(lg, dim=-1)
+        ids = torch.tensor(seqs, dtype=torch.long)
+        ref = logp.clone()
+        for p in procs:
+            ref = p(ids, ref)
+        ref = ref + torch.from_numpy(run.reshape(-1))[:, None]
+        top = torch.topk(ref, 2 * G, dim=-1)
+        for q in range(Q):
+            want_s, want_t = top.values[q].numpy(), top.indices[q].numpy()
+            fin = np.isfinite(want_s) & (want_s > -1e8)
+            got_s, got_t = cs[q], ct[q]
+            # ties between equal scores may be listed in either order: compare as sets of (token) with matching scores
+            assert sorted(got_t[fin].tolist()) == sorted(want_t[fin].tolist()), (step, q, got_t, want_t)
+            order_g, order_w = np.argsort(got_t[fin]), np.argsort(want_t[fin])
+            assert np.abs(got_s[fin][order_g] - want_s[fin][order_w]).max() < 1e-3, (step, q, got_s, want_s)
+            checked += int(fin.sum())
+        # continue with a real beam update: per audio the best G (sequence, token) pairs of this step, shuffled parents included
+        parents, nxt = np.zeros(Q, dtype=np.int32), np.zeros(Q, dtype=np.int32)
+        new_seqs, new_run = [], np.zeros((A, G), dtype=np.float32)
+        for a in range(A):
+            flat = [(float(cs[a * G + b, k]), a * G + b, int(ct[a * G + b, k])) for b in range(G) for k in range(2 * G) if ct[a * G + b, k] >= 0]
+            flat.sort(key=lambda x: -x[0])
+            pick = [f for f in flat if f[2] != S.EOS][:G]
+            rng.shuffle(pick)
+            for b, (sc, par, tok) in enumerate(pick):
+                parents[a * G + b], nxt[a * G + b] = par, tok
+                new_seqs.append(seqs[par] + [tok])
+                new_run[a, b] = sc
+        seqs, run = new_seqs, new_run
+        eng.decode_reorder(parents, nxt)
+    assert checked >= 6 * Q * 2

@@ -29,7 +29,7 @@ static int g_pdl_enabled = -1;  // BW_PDL (default on); cleared if a step with p
 
 size_t word_timestamps_work_floats(int Ha, int Tcap, int S);  // timestamps.cu
 int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
-                                 float time_precision, float* work, float* out_dev);
+                                 double time_precision, float* work, float* out_dev);
 
 namespace {
 
@@ -851,7 +851,7 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
 }
 
 int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
-                             float time_precision, float* out_host, int32_t out_pitch, void* stream) {
+                             double time_precision, float* out_host, int32_t out_pitch, void* stream) {
   BW_CHECK(e && e->finalized && audio && n_tokens && num_frames && out_host, "bw_word_timestamps_batch: bad arguments");
   BW_CHECK(e->cfg.n_align_heads > 0 && e->align, "bw_word_timestamps: engine built without alignment heads");
   BW_CHECK(n >= 1 && n <= e->cfg.max_audios, "bw_word_timestamps_batch: n=%d outside 1..%d", n, e->cfg.max_audios);
@@ -878,7 +878,7 @@ int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, cons
   return 0;
 }
 
-int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, float time_precision, float* out_host,
+int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, double time_precision, float* out_host,
                        void* stream) {
   return bw_word_timestamps_batch(e, 1, &audio, &n_tokens, &num_frames, time_precision, out_host, n_tokens + 1, stream);
 }

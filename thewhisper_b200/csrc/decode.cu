@@ -289,8 +289,17 @@ __global__ void __launch_bounds__(RL_THREADS) resid_ln_kernel(float* __restrict_
           const float4 bb = *reinterpret_cast<const float4*>(bias + k);
           v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
         }
-        for (int sp = 0; sp < nsplit; ++sp) {
-          const float4 pp = *reinterpret_cast<const float4*>(part + (long long)sp * split_stride + (long long)q * D + k);
+        const float* pq = part + (long long)q * D + k;
+        int sp = 0;
+        for (; sp + 3 < nsplit; sp += 4) {  // four splits' loads in flight together, added in split order
+          float4 pp[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pp[u] = *reinterpret_cast<const float4*>(pq + (long long)(sp + u) * split_stride);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { v[i].x += pp[u].x; v[i].y += pp[u].y; v[i].z += pp[u].z; v[i].w += pp[u].w; }
+        }
+        for (; sp < nsplit; ++sp) {
+          const float4 pp = *reinterpret_cast<const float4*>(pq + (long long)sp * split_stride);
           v[i].x += pp.x; v[i].y += pp.y; v[i].z += pp.z; v[i].w += pp.w;
         }
         *reinterpret_cast<float4*>(xr + k) = v[i];

@@ -33,16 +33,42 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// value i of a row that may be stored as nsplit raw split-K partial sums (fixed order: deterministic), + bias, * alpha
-__device__ __forceinline__ float split_sum(const float* __restrict__ p, long long idx, int nsplit, long long split_stride,
-                                           const float* __restrict__ bias, int bias_idx, float alpha) {
-  float v = p[idx];
+// 8 consecutive values of a row that may be stored as nsplit raw split-K partial sums ([split][row][col], split_stride apart):
+// summed in split order (deterministic), + bias, * alpha.  The loads of four splits are issued together: a dependent
+// load -> add -> load chain costs one L2 round trip per split (96 us for the self-attention kernel at Q = 64: profiles/r2c).
+__device__ __forceinline__ void split_sum8(const float* __restrict__ p, long long idx, int nsplit, long long split_stride,
+                                           const float* __restrict__ bias, int bias_idx, float alpha, float (&o)[8]) {
+  float4 a0 = *reinterpret_cast<const float4*>(p + idx), a1 = *reinterpret_cast<const float4*>(p + idx + 4);
   if (nsplit > 0) {
-    for (int s = 1; s < nsplit; ++s) v += p[(long long)s * split_stride + idx];
-    if (bias) v += bias[bias_idx];
-    v *= alpha;
+    int s = 1;
+    for (; s + 3 < nsplit; s += 4) {
+      float4 b0[4], b1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        b0[u] = *reinterpret_cast<const float4*>(p + (long long)(s + u) * split_stride + idx);
+        b1[u] = *reinterpret_cast<const float4*>(p + (long long)(s + u) * split_stride + idx + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0.x += b0[u].x; a0.y += b0[u].y; a0.z += b0[u].z; a0.w += b0[u].w;
+        a1.x += b1[u].x; a1.y += b1[u].y; a1.z += b1[u].z; a1.w += b1[u].w;
+      }
+    }
+    for (; s < nsplit; ++s) {
+      const float4 b0 = *reinterpret_cast<const float4*>(p + (long long)s * split_stride + idx);
+      const float4 b1 = *reinterpret_cast<const float4*>(p + (long long)s * split_stride + idx + 4);
+      a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+      a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+    }
+    if (bias) {
+      const float4 c0 = *reinterpret_cast<const float4*>(bias + bias_idx), c1 = *reinterpret_cast<const float4*>(bias + bias_idx + 4);
+      a0.x += c0.x; a0.y += c0.y; a0.z += c0.z; a0.w += c0.w;
+      a1.x += c1.x; a1.y += c1.y; a1.z += c1.z; a1.w += c1.w;
+    }
+    a0.x *= alpha; a0.y *= alpha; a0.z *= alpha; a0.w *= alpha;
+    a1.x *= alpha; a1.y *= alpha; a1.z *= alpha; a1.w *= alpha;
   }
-  return v;
+  o[0] = a0.x; o[1] = a0.y; o[2] = a0.z; o[3] = a0.w; o[4] = a1.x; o[5] = a1.y; o[6] = a1.z; o[7] = a1.w;
 }
 
 template <int NC, int R>
@@ -230,11 +256,16 @@ __device__ __forceinline__ float block_sum4(float v, float* red4) {
 
 // ------------------------------------------------------------------------------------------------
 // causal self-attention over cached positions 0..pos of one (sequence, head).  128 threads = 16 key groups x 8 lanes;
-// a lane owns 8 of the 64 head dims, so one warp-load covers 4 whole 128-byte K (or V) rows.  Keys are walked in
-// chunks of 128 with all 8 loads of a chunk in flight.
+// a lane owns 8 of the 64 head dims, so one warp-load covers 4 whole 128-byte K (or V) rows.  Keys are walked in chunks of 128
+// with an online softmax: 33 KB of static smem whatever Tmax is (the first version held all Tmax = 448 positions: 116 KB, ONE CTA
+// per SM, 43 waves at 320 sequences x 20 heads = 362 us per layer, profiles/r2c_summary.md); all loads of a chunk in flight together.
 // ------------------------------------------------------------------------------------------------
+constexpr int SCH = 128;
+
 __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
-  extern __shared__ __align__(16) uint8_t dyn[];  // K rows [Tmax][128 B] | V rows [Tmax][128 B] | scores [Tmax]
+  __shared__ __align__(16) uint8_t sK[SCH * 128];
+  __shared__ __align__(16) uint8_t sV[SCH * 128];
+  __shared__ float sc[SCH];
   __shared__ float red4[4];
   __shared__ float redo[16][64];
   const int h = blockIdx.x, q = blockIdx.y;
@@ -243,74 +274,80 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
   const int pos = *a.pos;
   const int n = pos + 1;
   const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  uint8_t* sK = dyn;
-  uint8_t* sV = dyn + (size_t)a.Tmax * 128;
-  float* sc = reinterpret_cast<float*>(dyn + (size_t)a.Tmax * 256);
-  // every K and V row of this (sequence, head) is requested now: one DRAM round trip for the whole kernel
-  const int n_cached = a.kc_w ? pos : n;  // batched path: the row of position `pos` comes from qkv, not from the cache
-  for (int s = grp; s < n_cached; s += 16) {
-    const int slot = a.anc ? a.anc[q * a.Tmax + s] : q;
-    const long long off = ((long long)slot * a.Tmax + s) * a.D + h * 64 + sub * 8;
-    cp_async16(sK + s * 128 + sub * 16, a.kc + off);
-    cp_async16(sV + s * 128 + sub * 16, a.vc + off);
-  }
-  if (a.kc_w && grp == (pos & 15)) {  // the group that reads row `pos` below appends it: k / v of this step, rounded to bf16
+  // batched path: k / v of this step come from the projection's output (qkv), are rounded to bf16, appended to the cache at
+  // position pos (a sequence's newest row lives in its own slot) and attended over; the GEMV path appended them itself
+  uint4 kw = make_uint4(0u, 0u, 0u, 0u), vw = kw;
+  const bool appender = a.kc_w && grp == (pos & 15);
+  if (appender) {
     const long long kidx = (long long)q * 3 * a.D + a.D + h * 64 + sub * 8;
     float kf[8], vf[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      kf[i] = split_sum(a.qkv, kidx + i, a.nsplit, a.split_stride, a.qkv_bias, a.D + h * 64 + sub * 8 + i, 1.0f);
-      vf[i] = split_sum(a.qkv, kidx + a.D + i, a.nsplit, a.split_stride, a.qkv_bias, 2 * a.D + h * 64 + sub * 8 + i, 1.0f);
-    }
-    uint4 kw, vw;
+    split_sum8(a.qkv, kidx, a.nsplit, a.split_stride, a.qkv_bias, a.D + h * 64 + sub * 8, 1.0f, kf);
+    split_sum8(a.qkv, kidx + a.D, a.nsplit, a.split_stride, a.qkv_bias, 2 * a.D + h * 64 + sub * 8, 1.0f, vf);
     kw.x = pack_bf16(kf[0], kf[1]); kw.y = pack_bf16(kf[2], kf[3]); kw.z = pack_bf16(kf[4], kf[5]); kw.w = pack_bf16(kf[6], kf[7]);
     vw.x = pack_bf16(vf[0], vf[1]); vw.y = pack_bf16(vf[2], vf[3]); vw.z = pack_bf16(vf[4], vf[5]); vw.w = pack_bf16(vf[6], vf[7]);
-    *reinterpret_cast<uint4*>(sK + pos * 128 + sub * 16) = kw;
-    *reinterpret_cast<uint4*>(sV + pos * 128 + sub * 16) = vw;
-    const long long off = ((long long)q * a.Tmax + pos) * a.D + h * 64 + sub * 8;  // a sequence's newest row lives in its own slot
+    const long long off = ((long long)q * a.Tmax + pos) * a.D + h * 64 + sub * 8;
     *reinterpret_cast<uint4*>(a.kc_w + off) = kw;
     *reinterpret_cast<uint4*>(a.vc_w + off) = vw;
   }
   float qv[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    qv[i] = split_sum(a.qkv, (long long)q * 3 * a.D + h * 64 + sub * 8 + i, a.nsplit, a.split_stride, a.qkv_bias, h * 64 + sub * 8 + i, a.q_alpha);
-  cp_async_wait_all();  // each thread reads back only what it copied itself
-  float lmax = -INFINITY;
-  for (int sb = 0; sb < n; sb += 16) {  // uniform trip count: the shuffles need all 32 lanes
-    const int s = sb + grp;
-    float d = 0.f;
-    if (s < n) {
-      float kf[8];
-      unpack8(*reinterpret_cast<const uint4*>(sK + s * 128 + sub * 16), kf);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d = fmaf(qv[j], kf[j], d);
-    }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 4);
-    if (s < n) {
-      if (sub == 0) sc[s] = d;
-      lmax = fmaxf(lmax, d);
-    }
-  }
-  const float mx = block_max4(lmax, red4);  // (also orders the sc[] writes before the reads below)
-  float lsum = 0.f;
-  for (int s = threadIdx.x; s < n; s += 128) {
-    const float e = __expf(sc[s] - mx);
-    sc[s] = e;
-    lsum += e;
-  }
-  const float inv = 1.0f / block_sum4(lsum, red4);
+  split_sum8(a.qkv, (long long)q * 3 * a.D + h * 64 + sub * 8, a.nsplit, a.split_stride, a.qkv_bias, h * 64 + sub * 8, a.q_alpha, qv);
+  float m_run = -INFINITY, l_run = 0.f;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int s = grp; s < n; s += 16) {
-    float vf[8];
-    unpack8(*reinterpret_cast<const uint4*>(sV + s * 128 + sub * 16), vf);
-    const float p = sc[s];
+  for (int c0 = 0; c0 < n; c0 += SCH) {
+    const int nc = min(SCH, n - c0);
+    __syncthreads();  // everybody is done with the previous chunk's rows and probabilities
+    for (int s = grp; s < nc; s += 16) {
+      const int ks = c0 + s;
+      if (a.kc_w && ks == pos) {  // (this thread is the appender: same group, same piece)
+        *reinterpret_cast<uint4*>(sK + s * 128 + sub * 16) = kw;
+        *reinterpret_cast<uint4*>(sV + s * 128 + sub * 16) = vw;
+      } else {
+        const int slot = a.anc ? a.anc[q * a.Tmax + ks] : q;
+        const long long off = ((long long)slot * a.Tmax + ks) * a.D + h * 64 + sub * 8;
+        cp_async16(sK + s * 128 + sub * 16, a.kc + off);
+        cp_async16(sV + s * 128 + sub * 16, a.vc + off);
+      }
+    }
+    cp_async_wait_all();  // each thread reads back only the 16-byte pieces it copied (or wrote) itself
+    float lmax = -INFINITY;
+    for (int sb = 0; sb < nc; sb += 16) {  // uniform trip count: the shuffles need all 32 lanes
+      const int s = sb + grp;
+      float d = 0.f;
+      if (s < nc) {
+        float kf[8];
+        unpack8(*reinterpret_cast<const uint4*>(sK + s * 128 + sub * 16), kf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
+        for (int j = 0; j < 8; ++j) d = fmaf(qv[j], kf[j], d);
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (s < nc) {
+        if (sub == 0) sc[s] = d;
+        lmax = fmaxf(lmax, d);
+      }
+    }
+    const float m_new = fmaxf(m_run, block_max4(lmax, red4));  // (also orders the sc[] writes before the reads below)
+    const float scale = __expf(m_run - m_new);                // first chunk: exp(-inf) = 0
+    float lsum = 0.f;
+    for (int s = threadIdx.x; s < nc; s += 128) {
+      const float e = __expf(sc[s] - m_new);
+      sc[s] = e;
+      lsum += e;
+    }
+    l_run = l_run * scale + block_sum4(lsum, red4);
+    m_run = m_new;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= scale;
+    for (int s = grp; s < nc; s += 16) {
+      float vf[8];
+      unpack8(*reinterpret_cast<const uint4*>(sV + s * 128 + sub * 16), vf);
+      const float p = sc[s];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) redo[grp][sub * 8 + j] = acc[j];
@@ -319,8 +356,9 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
     float o = 0.f;
 #pragma unroll
     for (int g = 0; g < 16; ++g) o += redo[g][threadIdx.x];
-    if (a.out_bf16) a.out_bf16[(long long)q * a.D + h * 64 + threadIdx.x] = __float2bfloat16(o * inv);
-    else a.out[(long long)q * a.D + h * 64 + threadIdx.x] = o * inv;
+    const float r = o / l_run;
+    if (a.out_bf16) a.out_bf16[(long long)q * a.D + h * 64 + threadIdx.x] = __float2bfloat16(r);
+    else a.out[(long long)q * a.D + h * 64 + threadIdx.x] = r;
   }
 }
 
@@ -365,11 +403,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
   float qv[GM][8];
 #pragma unroll
   for (int g = 0; g < GM; ++g) {
-    if (g < G) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        qv[g][j] = split_sum(a.q, (long long)(au * G + g) * a.D + h * 64 + sub * 8 + j, a.nsplit, a.split_stride, a.q_bias, h * 64 + sub * 8 + j, a.q_alpha);
-    }
+    if (g < G) split_sum8(a.q, (long long)(au * G + g) * a.D + h * 64 + sub * 8, a.nsplit, a.split_stride, a.q_bias, h * 64 + sub * 8, a.q_alpha, qv[g]);
   }
   const int slot = a.head_slots ? a.head_slots[h] : -1;
   float* align_row = nullptr;
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnA
   float* fold = red + GM * 4;
   const int h = blockIdx.x, au = blockIdx.y;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int G = (GM == 1) ? 1 : a.G;
+  const int G = (GM < MAXG) ? GM : a.G;  // exact instantiation for 1..5 beams; the MAXG one handles 6..8 with predicates
   const int S = a.S;
   const int ntiles = (S + XT - 1) / XT;
   const bf16* kbase = a.kc + ((long long)au * a.H + h) * S * 64;
@@ -541,8 +575,12 @@ __global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnA
   issue_tile(0, 0);
   pdl_wait();
   pdl_launch();
-  for (int i = t; i < G * 64; i += 128)
-    sq[i] = split_sum(a.q, (long long)(au * G + i / 64) * a.D + h * 64 + (i & 63), a.nsplit, a.split_stride, a.q_bias, h * 64 + (i & 63), a.q_alpha);
+  if (t < G * 8) {  // 8 values per thread: beam t / 8, dims (t % 8) * 8 ...
+    float qf[8];
+    split_sum8(a.q, (long long)(au * G + (t >> 3)) * a.D + h * 64 + (t & 7) * 8, a.nsplit, a.split_stride, a.q_bias, h * 64 + (t & 7) * 8, a.q_alpha, qf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq[(t >> 3) * 64 + (t & 7) * 8 + i] = qf[i];
+  }
   const int slot = a.head_slots ? a.head_slots[h] : -1;
   float* align_base = nullptr;
   if (slot >= 0 && a.align) {
@@ -706,14 +744,7 @@ int launch_gemv(cudaStream_t st, const GemvArgs& a) {
 }
 
 int launch_self_attn(cudaStream_t st, const SelfAttnArgs& a, int Q) {
-  const size_t smem = (size_t)a.Tmax * (256 + sizeof(float));
-  static bool attr = false;
-  if (!attr) {
-    BW_CUDA_OK(cudaFuncSetAttribute(self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
-  BW_CHECK(smem <= 200 * 1024, "self_attn: Tmax=%d too large", a.Tmax);
-  BW_CUDA_OK(launch_k(self_attn_kernel, dim3(a.H, Q), dim3(128), smem, st, a));
+  BW_CUDA_OK(launch_k(self_attn_kernel, dim3(a.H, Q), dim3(128), 0, st, a));
   return 0;
 }
 
@@ -733,14 +764,25 @@ int launch_cross_attn(cudaStream_t st, const CrossAttnArgs& a, int A) {
     const int stream_min = ev ? atoi(ev) : 296;
     if (stream_min > 0 && A * a.H >= stream_min) {
       auto smem_of = [](int gm) { return (size_t)4 * XT * 128 + (size_t)(gm * XT + gm * 64 + gm * 4 + 8 * gm * 64) * sizeof(float); };
-      static bool attr2 = false;
-      if (!attr2) {
-        BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(1)));
-        BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_stream_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(MAXG)));
-        attr2 = true;
+      // instantiated for the exact beam count (a bound of 8 with g < G predicates issued 8 / 5 of the instructions at beam 5)
+#define BW_XSTREAM(GMV)                                                                                                   \
+  {                                                                                                                       \
+    static bool attr_##GMV = false;                                                                                        \
+    if (!attr_##GMV) {                                                                                                     \
+      BW_CUDA_OK(cudaFuncSetAttribute(cross_attn_stream_kernel<GMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(GMV))); \
+      attr_##GMV = true;                                                                                                   \
+    }                                                                                                                     \
+    BW_CUDA_OK(launch_k(cross_attn_stream_kernel<GMV>, dim3(a.H, A), dim3(128), smem_of(GMV), st, a));                     \
+  }
+      switch (a.G) {
+        case 1: BW_XSTREAM(1) break;
+        case 2: BW_XSTREAM(2) break;
+        case 3: BW_XSTREAM(3) break;
+        case 4: BW_XSTREAM(4) break;
+        case 5: BW_XSTREAM(5) break;
+        default: BW_XSTREAM(8) break;
       }
-      if (a.G == 1) BW_CUDA_OK(launch_k(cross_attn_stream_kernel<1>, dim3(a.H, A), dim3(128), smem_of(1), st, a));
-      else BW_CUDA_OK(launch_k(cross_attn_stream_kernel<MAXG>, dim3(a.H, A), dim3(128), smem_of(MAXG), st, a));
+#undef BW_XSTREAM
       return 0;
     }
   }

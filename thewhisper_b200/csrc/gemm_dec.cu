@@ -6,7 +6,7 @@
 // 20-80 k-blocks through an 8-deep ring, i.e. 3-10 dependent DRAM round trips.  Here the operands are swapped and K is split:
 //   * the WEIGHT tile is the 128-row M operand of the MMA, the activations are the N operand (Q rounded up to 16, <= 256):
 //     a k-block costs 16 KB of W + Q x 128 B of X instead of 16 KB of zero-padded X + 4 KB of W, so 5-7 k-blocks fit in smem at once;
-//   * grid = (N / 128) x q-tiles x ksplit with ksplit chosen so that n-tiles x ksplit ~ 148 CTAs and a CTA's k-blocks fit its
+//   * grid = (N / 128) x q-tiles x ksplit with ksplit the smallest count that gives >= 64 CTAs and lets a CTA's k-blocks fit its
 //     ring: every byte a CTA needs is requested by ONE thread before anything is awaited -- one DRAM round trip per launch;
 //   * under programmatic dependent launch the weight boxes are requested BEFORE griddepcontrol.wait (weights do not depend on the
 //     previous kernel), the activation boxes after it;
@@ -196,11 +196,18 @@ DecGemmPlan gemm_dec_plan(int Q, int N, int K, int num_sms, bool want_split) {
   if (pl.stages > MAX_STAGES) pl.stages = MAX_STAGES;
   const int nk = K / DK;
   const int n_tiles = (N + DM - 1) / DM;
+  // as few splits as give (a) a CTA all of its k-blocks in one ring pass and (b) >= 64 CTAs: every extra split is another partial-sum
+  // row the consumer has to read (10-14 splits made resid_ln 9.5 us: profiles/r2c_summary.md)
   int ks = 1;
   if (want_split) {
-    ks = num_sms / (n_tiles * pl.q_tiles);
-    if (ks < 1) ks = 1;
+    const int ctas1 = n_tiles * pl.q_tiles;
+    const int ks_ring = (nk + pl.stages - 1) / pl.stages;
+    const int ks_fill = (64 + ctas1 - 1) / ctas1;
+    ks = ks_ring > ks_fill ? ks_ring : ks_fill;
+    const int ks_max = num_sms / ctas1 > 0 ? num_sms / ctas1 : 1;
+    if (ks > ks_max) ks = ks_max;
     if (ks > nk) ks = nk;
+    if (ks < 1) ks = 1;
   }
   pl.kper = (nk + ks - 1) / ks;
   pl.ksplit = (nk + pl.kper - 1) / pl.kper;

@@ -133,7 +133,7 @@ __global__ void ts_median_mean_kernel(float* __restrict__ work, const TsBatch b)
 }
 
 // anti-diagonal wavefront DTW for one audio, then a serial backtrace.  One block per audio of the batch.
-__global__ void __launch_bounds__(512) ts_dtw_kernel(float* __restrict__ work, const TsBatch b, float time_precision, float* __restrict__ out_all) {
+__global__ void __launch_bounds__(512) ts_dtw_kernel(float* __restrict__ work, const TsBatch b, double time_precision, float* __restrict__ out_all) {
   extern __shared__ float diag[];  // 3 x (Tcap + 2)
   const int item = blockIdx.x;
   const int T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(512) ts_dtw_kernel(float* __restrict__ work, c
   if (threadIdx.x == 0) {
     int i = T, j = NF;
     while (i > 0 || j > 0) {
-      out[i - 1 >= 0 ? i - 1 : 0] = (float)((double)(j - 1) * (double)time_precision);  // forward-first visit wins (overwrites)
+      out[i - 1 >= 0 ? i - 1 : 0] = (float)((double)(j - 1) * time_precision);  // float32(index * python float), as the reference stores it  // forward-first visit wins (overwrites)
       signed char tr;
       if (i == 0) tr = 2;
       else if (j == 0) tr = 1;
@@ -201,7 +201,7 @@ size_t word_timestamps_work_floats(int Ha, int Tcap, int S) {
 
 // n audios in one pass (4 launches whatever n is): items_dev [n][3] = (audio, T, NF); out_dev [n][Tcap + 8] seconds
 int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
-                                 float time_precision, float* work, float* out_dev) {
+                                 double time_precision, float* work, float* out_dev) {
   TsBatch b;
   b.items = items_dev;
   b.work_stride = (long long)word_timestamps_work_floats(Ha, Tcap, S);
