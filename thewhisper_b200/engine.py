@@ -176,6 +176,8 @@ class WhisperEngine:
         self._pcm_pin = torch.empty((max_audios, self.n_samples), dtype=torch.float32).pin_memory()
         self._tok_host = np.zeros((max_audios * max_beams, dims.max_target_positions), dtype=np.int32)
         self._keep = None
+        # work counters (bench / diagnostics): the timestamp `seek` loop may encode and decode a chunk more than once
+        self.stats = {"encode_calls": 0, "chunks_encoded": 0, "decode_steps": 0, "sequence_steps": 0}
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -240,6 +242,8 @@ class WhisperEngine:
 
     def encode(self, B: int) -> None:
         _lib.check(self.lib.bw_encode(self.h, B, self._stream()))
+        self.stats["encode_calls"] += 1
+        self.stats["chunks_encoded"] += B
 
     def encoder_output(self, B: int) -> torch.Tensor:
         return self.buffer("enc_out", torch.bfloat16, (self.max_audios, self.S, self.dims.d_model))[:B].float()
@@ -269,6 +273,8 @@ class WhisperEngine:
 
     def decode_run(self, n_steps: int) -> None:
         _lib.check(self.lib.bw_decode_run(self.h, n_steps, self._stream()))
+        self.stats["decode_steps"] += n_steps
+        self.stats["sequence_steps"] += n_steps * self._Q
 
     def decode_kernel_launches(self) -> int:
         """Kernels launched by decode_run so far (counted from the captured step graphs)."""

@@ -170,12 +170,18 @@ class ASRPipeline:
                 flat.append({"input": idx, "audio": chunk, "stride": stride})
         per_input: List[List[dict]] = [[] for _ in items]
         n_samples = self.engine.n_samples
+        import time as _time
+
+        tm = {"windows_s": 0.0, "generate_s": 0.0, "decode_asr_s": 0.0}  # host wall clock per phase of this call (diagnostics)
+        t_ph = _time.perf_counter()
         for b0 in range(0, len(flat), batch_size):
             group = flat[b0:b0 + batch_size]
             B = len(group)
             pcm = np.stack([pad_or_trim(g["audio"], n_samples) for g in group])
             num_frames = np.asarray([num_valid_frames(len(g["audio"]), n_samples) for g in group], dtype=np.int64)
             mel = self.engine.logmel(pcm, return_f32=True)
+            tm["windows_s"] += _time.perf_counter() - t_ph
+            t_ph = _time.perf_counter()
             out = self.generator.generate(
                 B, num_frames=num_frames, mel_f32=mel, return_timestamps=bool(return_timestamps),
                 return_token_timestamps=(return_timestamps == "word"), language=generate_kwargs.get("language"),
@@ -188,6 +194,8 @@ class ASRPipeline:
                     ln, sl, sr = g["stride"]
                     o["stride"] = (ln / SAMPLE_RATE, sl / SAMPLE_RATE, sr / SAMPLE_RATE)
                 per_input[g["input"]].append(o)
+            tm["generate_s"] += _time.perf_counter() - t_ph
+            t_ph = _time.perf_counter()
 
         # ---- tokens -> text (+ chunks): string-side state machine of the installed tokenizer
         time_precision = self.feature_extractor.chunk_length / self.engine.S
@@ -196,4 +204,6 @@ class ASRPipeline:
             text, optional = self.tokenizer._decode_asr(outs, return_timestamps=return_timestamps, return_language=return_language,
                                                         time_precision=time_precision)
             results.append({"text": text, **optional})
+        tm["decode_asr_s"] = _time.perf_counter() - t_ph
+        self.last_timing = tm
         return results if is_list else results[0]

@@ -105,19 +105,25 @@ def run_batch(name: str, chunks: int, beams: int, word_ts: bool, new_tokens: int
     audios = [S.synth_audio(chunk_s, seed=3000 + i) for i in range(chunks)]
     gk = {"num_beams": beams, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": new_tokens}
     kw = {"return_timestamps": "word"} if word_ts else {}
-    times = []
+    times, work = [], {}
     for it in range(1 + reps):
+        st0 = dict(getattr(pipe.engine, "stats", {}))
         _sync()
         t0 = time.perf_counter()
         out = pipe(audios, batch_size=chunks, generate_kwargs=dict(gk), **kw)
         _sync()
         times.append(time.perf_counter() - t0)
+        work = {k: v - st0.get(k, 0) for k, v in getattr(pipe.engine, "stats", {}).items()}
+        work.update({k: round(v, 4) for k, v in getattr(pipe, "last_timing", {}).items()})
     dt = float(np.median(times[1:]))
     assert len(out) == chunks
     line = {"config": name, "chunks": chunks, "chunk_s": chunk_s, "beams": beams, "word_timestamps": word_ts,
             "new_tokens_per_chunk": new_tokens, "seconds_per_batch": dt, "tokens_per_sec": chunks * new_tokens / dt,
             "rtfx": chunks * chunk_s / dt, "preset": preset, "engine": "stub (plumbing check)" if stub else "b200",
-            "api": "ASRPipeline.__call__(list of host arrays)"}
+            "api": "ASRPipeline.__call__(list of host arrays)",
+            # what one call really ran: with timestamp rules on, a random checkpoint closes segments early and the reference's `seek`
+            # loop re-encodes and re-decodes the rest of the chunk (generation_whisper.py:785-903) -- more passes than chunks
+            "work_per_call": work}
     st = _step_time_ms(pipe, chunks, beams, word_ts)
     if st:
         ms, t_mean = st

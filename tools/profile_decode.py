@@ -105,7 +105,8 @@ def main():
         gb = (2.0 * (L * (6 * d * d + 2 * d * ffn) + V * d) + A * 2.0 * L * 2 * eng.S * d + A * G * 2.0 * L * 2 * 68 * d) / 1e9
         print(f"decode step (A={A} G={G} S={eng.S}): {us:.1f} us, {A * 1e6 / us:.0f} tok/s, algorithmic {gb:.2f} GB/step -> {gb / us * 1e6:.0f} GB/s")
     toks, fin, pos = eng.decode_read()
-    print("pos", pos, "tokens", toks[0, :12].tolist())
+    fl = eng.lib.bw_runtime_flags()
+    print("pos", pos, "tokens", toks[0, :12].tolist(), "| cooperative launch", bool(fl & 1), "| programmatic dependent launch", bool(fl & 2))
 
 
 if __name__ == "__main__":
