@@ -27,10 +27,12 @@
 extern "C" {
 #endif
 
-#define BW_ABI_VERSION 1
+#define BW_ABI_VERSION 2
 
 typedef struct bw_engine bw_engine;
 
+#ifndef THEWHISPER_B200_TYPES_
+#define THEWHISPER_B200_TYPES_
 typedef struct bw_config {
   int32_t d_model;      /* 1280 */
   int32_t n_heads;      /* 20  (head_dim must be 64) */
@@ -45,6 +47,8 @@ typedef struct bw_config {
   int32_t max_beams;    /* G <= 8 sequences sharing one audio's cross K/V */
   int32_t n_align_heads;/* alignment heads for word timestamps (0 = off) */
   int32_t max_align_steps; /* rows of alignment scores kept per audio (<= max_target_positions) */
+  int32_t dtype;        /* 16-bit element type of weights / activations / KV caches: 0 = bfloat16, 1 = float16 (what the reference's
+                           streaming and benchmark paths run: REF streaming_pipeline.py:369-370); accumulation is fp32 in both */
 } bw_config;
 
 typedef struct bw_decode_opts {
@@ -56,6 +60,7 @@ typedef struct bw_decode_opts {
   const int32_t* begin_suppress_tokens; int32_t n_begin_suppress;
   int32_t record_alignment;   /* 1 = keep cross-attention scores of the alignment heads */
 } bw_decode_opts;
+#endif /* THEWHISPER_B200_TYPES_ */
 
 const char* bw_last_error(void);
 int bw_abi_version(void);
@@ -68,7 +73,7 @@ int bw_runtime_flags(void);
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
 int bw_engine_create(const bw_config* cfg, bw_engine** out);
 void bw_engine_destroy(bw_engine* e);
-/* Bind one weight tensor by name (device pointer, must outlive the engine).  Matrices are bf16 row-major
+/* Bind one weight tensor by name (device pointer, must outlive the engine).  Matrices are 16-bit (bw_config::dtype) row-major
  * [out, in] (torch Linear layout), vectors fp32.  Names: see DESIGN.md "weights". */
 int bw_engine_set_tensor(bw_engine* e, const char* name, const void* device_ptr);
 /* slaney mel filter bank [201, n_mels] fp32 on the HOST (TF/audio_utils.py:453-544), copied to the device. */

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/thewhisper_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, (sorted(set(names) ^ set(_lib.SYMBOLS)))
-    assert lib.bw_abi_version() == 1
+    assert lib.bw_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -37,7 +37,7 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = _lib.load()
-    cfg = _lib.bw_config(128, 2, 512, 2, 2, 128, 51866, 500, 448, 1, 1, 0, 448)
+    cfg = _lib.bw_config(128, 2, 512, 2, 2, 128, 51866, 500, 448, 1, 1, 0, 448, 0)
     h = C.c_void_p()
     rc = lib.bw_engine_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and b"no CUDA device" in lib.bw_last_error()

@@ -20,7 +20,7 @@ class BwError(RuntimeError):
 class bw_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "d_model", "n_heads", "ffn", "enc_layers", "dec_layers", "n_mels", "vocab", "max_source_positions",
-        "max_target_positions", "max_audios", "max_beams", "n_align_heads", "max_align_steps")]
+        "max_target_positions", "max_audios", "max_beams", "n_align_heads", "max_align_steps", "dtype")]
 
 
 class bw_decode_opts(C.Structure):
@@ -93,7 +93,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the export is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.bw_abi_version() != 1:
+    if lib.bw_abi_version() != 2:
         raise BwError("ABI version mismatch")
     _lib = lib
     return lib

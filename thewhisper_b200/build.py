@@ -14,8 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libthewhisper_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_dec.cu", "attn_enc.cu", "logmel.cu", "decode.cu", "decode_stream.cu", "decode_mega.cu", "timestamps.cu", "hostproc.cu"]
-HEADERS = ["common.cuh", "kernels.h", "decode.cuh", "decode_mega_common.cuh", os.path.join("..", "..", "include", "thewhisper_b200.h")]
+# compiled twice: 16-bit elements = bfloat16 (x.o) and, with -DBW_F16, = float16 (x_f16.o)
+SOURCES_PER_DTYPE = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_dec.cu", "attn_enc.cu", "logmel.cu", "decode.cu", "decode_stream.cu",
+                     "decode_mega.cu", "timestamps.cu"]
+SOURCES_ONCE = ["abi.cu", "hostproc.cu"]
+HEADERS = ["common.cuh", "kernels.h", "decode.cuh", "decode_mega_common.cuh", "abi_rename.h", "abi_unrename.h",
+           os.path.join("..", "..", "include", "thewhisper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -39,12 +43,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     objs, jobs = [], []
-    for src in SOURCES:
+    units = [(src, "", []) for src in SOURCES_ONCE + SOURCES_PER_DTYPE] + [(src, "_f16", ["-DBW_F16"]) for src in SOURCES_PER_DTYPE]
+    for src, suffix, defs in units:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(OUT_DIR, src.replace(".cu", suffix + ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return r.stderr
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             for log in ex.map(run, jobs):
                 if verbose and log:
                     print(log)

@@ -10,11 +10,21 @@
 #include <tuple>
 #include <vector>
 
+// This file is compiled once per element type (bf16: namespace bw, symbols *_bf16; -DBW_F16: namespace bw_f16, symbols *_f16);
+// abi.cu defines the public names of include/thewhisper_b200.h and dispatches on bw_config::dtype.
+#ifdef BW_F16
+#define BW_RENAME_SUFFIX _f16
+#define BW_API_NS bw_api_f16
+#else
+#define BW_RENAME_SUFFIX _bf16
+#define BW_API_NS bw_api
+#endif
+#include "abi_rename.h"
 #include "../../include/thewhisper_b200.h"
 #include "decode.cuh"
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -55,7 +65,7 @@ struct GraphKey {
 }  // namespace
 }  // namespace bw
 
-using namespace bw;
+using namespace BW_NS;
 
 struct bw_engine {
   bw_config cfg;
@@ -108,7 +118,7 @@ struct bw_engine {
   std::map<std::string, std::pair<void*, size_t>> buffers;
 };
 
-namespace bw_api {
+namespace BW_API_NS {
 
 template <typename T>
 int dalloc(bw_engine* e, const char* name, T** p, size_t count, bool zero = true) {
@@ -468,7 +478,7 @@ __global__ void mel_to_tm_kernel(const float* __restrict__ mel, bf16* __restrict
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int f = f0 + i, m = m0 + tx;
-    if (f < frames && m < n_mels) out[((long long)b * (frames + 2) + f + 1) * n_mels + m] = __float2bfloat16(tile[tx][i]);
+    if (f < frames && m < n_mels) out[((long long)b * (frames + 2) + f + 1) * n_mels + m] = f2e(tile[tx][i]);
   }
 }
 
@@ -492,12 +502,12 @@ __global__ void reorder_kernel(const int* __restrict__ anc_old, int* __restrict_
   }
 }
 
-}  // namespace bw_api
-using namespace bw_api;
+}  // namespace BW_API_NS
+using namespace BW_API_NS;
 
 extern "C" {
 
-const char* bw_last_error(void) { return bw::get_error(); }
+const char* bw_last_error(void) { return BW_NS::get_error(); }
 int bw_abi_version(void) { return BW_ABI_VERSION; }
 int bw_runtime_flags(void) { return (g_mega_coop == 1 ? 1 : 0) | (g_pdl_enabled == 1 ? 2 : 0); }
 int bw_device_count(void) {

@@ -14,7 +14,7 @@
 // Keys beyond S (tile overrun into the next row block / TMA zero fill) are masked to -inf before the max.
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -244,13 +244,13 @@ __global__ void attn_enc_simt_kernel(const bf16* __restrict__ qkv, bf16* __restr
   __shared__ float red[32];
   const int q = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const bf16* base = qkv + (long long)b * S * 3 * D;
-  if (threadIdx.x < DH) qs[threadIdx.x] = __bfloat162float(base[(long long)q * 3 * D + h * DH + threadIdx.x]);
+  if (threadIdx.x < DH) qs[threadIdx.x] = e2f(base[(long long)q * 3 * D + h * DH + threadIdx.x]);
   __syncthreads();
   float lmax = -INFINITY;
   for (int k = threadIdx.x; k < S; k += blockDim.x) {
     const bf16* kp = base + (long long)k * 3 * D + D + h * DH;
     float a = 0.f;
-    for (int d = 0; d < DH; ++d) a = fmaf(qs[d], __bfloat162float(kp[d]), a);
+    for (int d = 0; d < DH; ++d) a = fmaf(qs[d], e2f(kp[d]), a);
     a *= scale;
     sc[k] = a;
     lmax = fmaxf(lmax, a);
@@ -274,8 +274,8 @@ __global__ void attn_enc_simt_kernel(const bf16* __restrict__ qkv, bf16* __restr
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
   if (threadIdx.x < DH) {
     float a = 0.f;
-    for (int k = 0; k < S; ++k) a = fmaf(sc[k], __bfloat162float(base[(long long)k * 3 * D + 2 * D + h * DH + threadIdx.x]), a);
-    out[((long long)(b * S + q)) * D + h * DH + threadIdx.x] = __float2bfloat16(a / tot);
+    for (int k = 0; k < S; ++k) a = fmaf(sc[k], e2f(base[(long long)k * 3 * D + 2 * D + h * DH + threadIdx.x]), a);
+    out[((long long)(b * S + q)) * D + h * DH + threadIdx.x] = f2e(a / tot);
   }
 }
 
@@ -285,7 +285,7 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restric
   const int s0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   for (int i = threadIdx.x; i < 64 * DH; i += blockDim.x) {
     const int s = i / DH, d = i % DH;
-    tile[s][d] = (s0 + s < S) ? qkv[((long long)(b * S + s0 + s)) * 3 * D + 2 * D + h * DH + d] : __float2bfloat16(0.f);
+    tile[s][d] = (s0 + s < S) ? qkv[((long long)(b * S + s0 + s)) * 3 * D + 2 * D + h * DH + d] : f2e(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * DH; i += blockDim.x) {

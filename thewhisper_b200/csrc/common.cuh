@@ -3,13 +3,36 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
-namespace bw {
+// Every kernel source is compiled twice: once with 16-bit elements = bfloat16 (namespace bw) and once, with -DBW_F16, = IEEE half
+// (namespace bw_f16) -- the reference's streaming / benchmark paths run fp16 (REF streaming_pipeline.py:369-370).  Same byte cost,
+// same tcgen05 kind::f16 instructions (the operand format is a field of the instruction descriptor); accumulation, softmax,
+// LayerNorm and the residual stream are fp32 in both.  `bf16` below is the historical name of "the engine's 16-bit element type".
+#ifdef BW_F16
+#define BW_NS bw_f16
+#define BW_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define BW_UMMA_FMT 0u  // tcgen05 instruction-descriptor a/b format: F16
+#else
+#define BW_NS bw
+#define BW_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define BW_UMMA_FMT 1u  // BF16
+#endif
 
+namespace BW_NS {
+
+#ifdef BW_F16
+typedef __half bf16;
+__host__ __device__ __forceinline__ bf16 f2e(float x) { return __float2half_rn(x); }
+__host__ __device__ __forceinline__ float e2f(bf16 x) { return __half2float(x); }
+#else
 typedef __nv_bfloat16 bf16;
+__host__ __device__ __forceinline__ bf16 f2e(float x) { return __float2bfloat16(x); }
+__host__ __device__ __forceinline__ float e2f(bf16 x) { return __bfloat162float(x); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -20,14 +43,14 @@ const char* get_error();
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
     if (_e != cudaSuccess) {                                                                   \
-      bw::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      BW_NS::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
       return -1;                                                                               \
     }                                                                                          \
   } while (0)
 #define BW_CHECK(cond, ...)                                                                    \
   do {                                                                                         \
     if (!(cond)) {                                                                             \
-      bw::set_error(__VA_ARGS__);                                                              \
+      BW_NS::set_error(__VA_ARGS__);                                                              \
       return -2;                                                                               \
     }                                                                                          \
   } while (0)
@@ -52,6 +75,16 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact (erf) GELU, as torch.nn.functional.gelu(approximate="none")
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+#ifdef BW_F16
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __half2 t = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(t);
+}
+#else
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -60,6 +93,7 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
+#endif
 
 // 16-byte streaming load that does not pollute L1 (weights / KV are read once per step)
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
@@ -191,10 +225,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (InstrDescriptor in the same header): c_format F32=1 @4, a/b format BF16=1 @7/@10,
+// instruction descriptor (InstrDescriptor in the same header): c_format F32=1 @4, a/b format (F16=0, BF16=1) @7/@10,
 // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (BW_UMMA_FMT << 7) | (BW_UMMA_FMT << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (lane i of warp w reads TMEM

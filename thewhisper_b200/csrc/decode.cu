@@ -10,7 +10,7 @@
 #include "decode.cuh"
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -23,7 +23,7 @@ __global__ void embed_kernel(const bf16* __restrict__ E, const float* __restrict
   const int pos = *pos_ptr;
   const int tok = tokens[q * Tmax + pos];
   for (int d = threadIdx.x; d < D; d += blockDim.x)
-    x[(long long)q * D + d] = __bfloat162float(E[(long long)tok * D + d]) + P[(long long)pos * D + d];
+    x[(long long)q * D + d] = e2f(E[(long long)tok * D + d]) + P[(long long)pos * D + d];
 }
 
 // ------------------------------------------------------------------------------------------------

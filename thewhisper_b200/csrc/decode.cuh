@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-namespace bw {
+namespace BW_NS {
 
 // out[m, n] = epi( LN?(x[m, :]) . W[n, :] )   for m < M <= 8 rows per launch
 struct GemvArgs {

@@ -26,7 +26,7 @@
 // Token selection stays a separate small kernel.
 #include "decode_mega_common.cuh"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -316,8 +316,8 @@ __device__ __forceinline__ void finish_rows(const GemvDesc& d, const float (&acc
     d.out[(long long)m * d.ldo + nn] = v;
     if (d.kc && nn >= D) {
       const long long row = ((long long)m * Tmax + pos) * D;
-      if (nn < 2 * D) d.kc[row + nn - D] = __float2bfloat16(v);
-      else d.vc[row + nn - 2 * D] = __float2bfloat16(v);
+      if (nn < 2 * D) d.kc[row + nn - D] = f2e(v);
+      else d.vc[row + nn - 2 * D] = f2e(v);
     }
   }
 }
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(const __grid_constan
     for (int i = threadIdx.x; i < Q * D; i += MT) {
       const int q = i / D, d = i - q * D;
       const int tok = a.tokens[q * a.Tmax + pos];
-      a.dx[i] = __bfloat162float(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
+      a.dx[i] = e2f(a.embed[(long long)tok * D + d]) + a.dec_pos[(long long)pos * D + d];
     }
   }
   bar.sync();

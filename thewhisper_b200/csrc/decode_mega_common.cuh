@@ -8,7 +8,7 @@
 #include "decode.cuh"
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 namespace mega {
 
 constexpr int MT = 384;        // threads per CTA (12 warps: <= 170 registers per thread)

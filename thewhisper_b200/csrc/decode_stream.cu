@@ -11,7 +11,7 @@
 #include "decode.cuh"
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(const GemvArgs a, co
         a.out[(long long)mg * a.ldo + nn] = v;
         if (a.kc && nn >= a.D) {
           const long long row = ((long long)(a.seq0 + mg) * a.Tmax + pos) * a.D;
-          if (nn < 2 * a.D) a.kc[row + nn - a.D] = __float2bfloat16(v);
-          else a.vc[row + nn - 2 * a.D] = __float2bfloat16(v);
+          if (nn < 2 * a.D) a.kc[row + nn - a.D] = f2e(v);
+          else a.vc[row + nn - 2 * a.D] = f2e(v);
         }
       }
       if (PIPE) {
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnArgs a) {
 #pragma unroll
     for (int g = 0; g < 16; ++g) o += redo[g][threadIdx.x];
     const float r = o / l_run;
-    if (a.out_bf16) a.out_bf16[(long long)q * a.D + h * 64 + threadIdx.x] = __float2bfloat16(r);
+    if (a.out_bf16) a.out_bf16[(long long)q * a.D + h * 64 + threadIdx.x] = f2e(r);
     else a.out[(long long)q * a.D + h * 64 + threadIdx.x] = r;
   }
 }
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
           o = fmaf(__ldcg(&a.part_o[(hb + (long long)sp * G + g) * 64 + d]), w, o);
         }
       }
-      if (a.out_bf16) a.out_bf16[(long long)(au * G + g) * a.D + h * 64 + d] = __float2bfloat16(o / L);
+      if (a.out_bf16) a.out_bf16[(long long)(au * G + g) * a.D + h * 64 + d] = f2e(o / L);
       else a.out[(long long)(au * G + g) * a.D + h * 64 + d] = o / L;
     }
   }
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnA
     const float l = (red[g * 4] + red[g * 4 + 1]) + (red[g * 4 + 2] + red[g * 4 + 3]);
     const float r = acc / l;
     const long long off = (long long)(au * G + g) * a.D + h * 64 + d;
-    if (a.out_bf16) a.out_bf16[off] = __float2bfloat16(r);
+    if (a.out_bf16) a.out_bf16[off] = f2e(r);
     else a.out[off] = r;
   }
 }

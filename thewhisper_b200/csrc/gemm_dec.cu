@@ -19,7 +19,7 @@
 
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -149,7 +149,7 @@ gemm_dec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (e.act == 1) f = gelu_erf(f);
             const long long off = (long long)(q0 + q) * e.row_stride;
             if (of) of[off] = f;
-            else ob[off] = __float2bfloat16(f);
+            else ob[off] = f2e(f);
           }
         }
       }

@@ -14,7 +14,7 @@
 
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 
@@ -226,8 +226,8 @@ __global__ void gemm_simt_kernel(GemmA a, const bf16* __restrict__ W, GemmParams
   float acc = 0.f;
   const int kend = (p.epi.n_valid > 0 && n >= p.epi.n_valid) ? 0 : p.K;  // rows of W beyond n_valid do not exist: zero
   for (int k = 0; k < kend; ++k) {
-    const float av = __bfloat162float(ab[(long long)(t + k / p.kwrap) * a.pitch + (k % p.kwrap)]);
-    acc = fmaf(av, __bfloat162float(w[k]), acc);
+    const float av = e2f(ab[(long long)(t + k / p.kwrap) * a.pitch + (k % p.kwrap)]);
+    acc = fmaf(av, e2f(w[k]), acc);
   }
   const GemmEpi& e = p.epi;
   const long long off = (long long)b * e.batch_stride + (long long)t * e.row_stride + (long long)(n >> 6) * e.head_stride + (n & 63);
@@ -237,7 +237,7 @@ __global__ void gemm_simt_kernel(GemmA a, const bf16* __restrict__ W, GemmParams
   if (e.pos) acc += e.pos[(long long)t * p.N + n];
   if (e.residual) acc += e.residual[off];
   if (e.out_f32) e.out_f32[off] = acc;
-  else e.out_bf16[off] = __float2bfloat16(acc);
+  else e.out_bf16[off] = f2e(acc);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -275,7 +275,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = fn(out, BW_TMAP_DTYPE, 2, const_cast<void*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BW_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%llu cols=%llu pitch=%llu box=%ux%u) -> %d",
@@ -291,7 +291,7 @@ static int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch,
   cuuint64_t strides[2] = {row_pitch_bytes, batch_pitch_bytes};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = fn(out, BW_TMAP_DTYPE, 3, const_cast<void*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BW_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d batch=%llu rows=%llu cols=%llu pitch=%llu/%llu) -> %d",

@@ -20,7 +20,7 @@
 
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 

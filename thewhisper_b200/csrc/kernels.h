@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-namespace bw {
+namespace BW_NS {
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM: C[b,t,n] = epilogue( sum_k A(b,t,k) * W[n,k] ), bf16 operands, fp32 accumulate in TMEM

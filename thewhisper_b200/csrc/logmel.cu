@@ -18,7 +18,7 @@
 
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 constexpr int NFFT = 400;
@@ -182,14 +182,14 @@ __global__ void logmel_finalize_kernel(const float* __restrict__ scratch, const 
     if (f < frames) {
       v = scratch[((long long)b * frames + f) * n_mels + mth];
       v = (fmaxf(v, floor_v) + 4.0f) / 4.0f;
-      out_tm[((long long)b * (frames + 2) + f + 1) * n_mels + mth] = __float2bfloat16(v);
+      out_tm[((long long)b * (frames + 2) + f + 1) * n_mels + mth] = f2e(v);
     }
     if (mth < 128) tile[ff][mth] = v;
   }
   if (blockIdx.x == 0) {  // zero the two padding rows
     for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
-      out_tm[((long long)b * (frames + 2)) * n_mels + i] = __float2bfloat16(0.f);
-      out_tm[((long long)b * (frames + 2) + frames + 1) * n_mels + i] = __float2bfloat16(0.f);
+      out_tm[((long long)b * (frames + 2)) * n_mels + i] = f2e(0.f);
+      out_tm[((long long)b * (frames + 2) + frames + 1) * n_mels + i] = f2e(0.f);
     }
   }
   if (out_f32) {

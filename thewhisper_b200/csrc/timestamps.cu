@@ -12,7 +12,7 @@
 
 #include "kernels.h"
 
-namespace bw {
+namespace BW_NS {
 
 namespace {
 

@@ -61,14 +61,25 @@ def interpolate_positions(table: torch.Tensor, chunk_length_s: float) -> torch.T
     return out.squeeze(0).t().contiguous()
 
 
-def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, enc_pos: torch.Tensor, device: torch.device) -> Dict[str, torch.Tensor]:
+ENGINE_DTYPES = {torch.bfloat16: 0, torch.float16: 1}
+
+
+def engine_dtype(torch_dtype) -> torch.dtype:
+    """The 16-bit element type the engine runs for a caller's `torch_dtype` (REF nvidia/asr_pipeline.py:39: None = the checkpoint's
+    fp32): float16 -> float16 (what the reference's streaming and benchmark paths use), bfloat16 / None / float32 -> bfloat16.
+    Accumulation, softmax, LayerNorm and the residual stream are fp32 in both; there is no fp32-operand mode."""
+    return torch.float16 if torch_dtype == torch.float16 else torch.bfloat16
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], dims: ModelDims, enc_pos: torch.Tensor, device: torch.device,
+                 dtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
     """HF WhisperForConditionalGeneration state_dict -> named device tensors in the engine's layouts
-    (bf16 [out, in] matrices, fp32 vectors; q/k/v fused; conv kernels reordered to [co][tap][ci])."""
+    (16-bit [out, in] matrices in `dtype`, fp32 vectors; q/k/v fused; conv kernels reordered to [co][tap][ci])."""
     D = dims.d_model
     out: Dict[str, torch.Tensor] = {}
 
     def mat(t):
-        return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+        return t.detach().to(device=device, dtype=dtype).contiguous()
 
     def vec(t):
         return t.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -137,7 +148,7 @@ class WhisperEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], dims: ModelDims, chunk_length_s: float = 30,
                  device: str = "cuda:0", max_audios: int = 1, max_beams: int = 1,
                  alignment_heads: Optional[Sequence[Sequence[int]]] = None, max_align_steps: int = 448,
-                 weights: Optional[Dict[str, torch.Tensor]] = None):
+                 weights: Optional[Dict[str, torch.Tensor]] = None, dtype: torch.dtype = torch.bfloat16):
         self.lib = _lib.load()
         if not torch.cuda.is_available() or self.lib.bw_device_count() == 0:
             raise _lib.BwError("no CUDA device visible: thewhisper_b200 has no CPU fallback")
@@ -155,11 +166,19 @@ class WhisperEngine:
         if weights is None:
             table = state_dict["model.encoder.embed_positions.weight"]
             enc_pos = table.detach().float().cpu() if table.shape[0] == S else interpolate_positions(table, chunk_length_s)
-            weights = pack_weights(state_dict, dims, enc_pos, self.device)
+            weights = pack_weights(state_dict, dims, enc_pos, self.device, dtype)
+        else:  # preloaded: the matrices decide (all 16-bit tensors share one type)
+            mats = {t.dtype for t in weights.values() if t.dtype in ENGINE_DTYPES}
+            if len(mats) != 1:
+                raise _lib.BwError(f"preloaded weights must hold matrices of exactly one 16-bit type, got {mats}")
+            dtype = mats.pop()
+        if dtype not in ENGINE_DTYPES:
+            raise _lib.BwError(f"engine dtype must be torch.bfloat16 or torch.float16, got {dtype}")
+        self.dtype = dtype
         self.weights = weights  # keeps the device memory alive
         cfg = _lib.bw_config(dims.d_model, dims.n_heads, dims.ffn, dims.enc_layers, dims.dec_layers, dims.n_mels,
                              dims.vocab, S, dims.max_target_positions, max_audios, max_beams,
-                             len(self.alignment_heads), min(max_align_steps, dims.max_target_positions))
+                             len(self.alignment_heads), min(max_align_steps, dims.max_target_positions), ENGINE_DTYPES[dtype])
         self.max_align_steps = cfg.max_align_steps
         h = C.c_void_p()
         _lib.check(self.lib.bw_engine_create(C.byref(cfg), C.byref(h)))
@@ -246,7 +265,7 @@ class WhisperEngine:
         self.stats["chunks_encoded"] += B
 
     def encoder_output(self, B: int) -> torch.Tensor:
-        return self.buffer("enc_out", torch.bfloat16, (self.max_audios, self.S, self.dims.d_model))[:B].float()
+        return self.buffer("enc_out", self.dtype, (self.max_audios, self.S, self.dims.d_model))[:B].float()
 
     # ------------------------------------------------------------------------------------------
     def decode_begin(self, prompts: np.ndarray, A: int, G: int, opts: DecodeOptions, begin_index: Optional[int] = None) -> None:

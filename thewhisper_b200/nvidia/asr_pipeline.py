@@ -21,7 +21,7 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from ..engine import ModelDims, WhisperEngine
+from ..engine import ModelDims, WhisperEngine, engine_dtype
 from ..features import SAMPLE_RATE, num_valid_frames, pad_or_trim
 from ..generation import GenerationSettings, WhisperGenerator
 from ..hostproc import chunk_windows, install_merge
@@ -53,6 +53,15 @@ class ASRPipeline:
         if chunk_length_s not in (10, 15, 20, 30):
             raise ValueError(f"chunk_length_s={chunk_length_s} is not supported (10, 15, 20 or 30)")
         self.chunk_length_s = chunk_length_s
+        # torch_dtype picks the engine's 16-bit element type: float16 as the reference's streaming / benchmark paths pass it, else
+        # bfloat16 (None / float32 = the reference's default fp32 model: the engine has no fp32-operand mode and says so once)
+        self.torch_dtype = torch_dtype
+        self.engine_dtype = engine_dtype(torch_dtype if torch_dtype is not None else getattr(model, "dtype", None))
+        if torch_dtype in (None, torch.float32) and getattr(model, "dtype", torch.float32) == torch.float32:
+            import warnings
+
+            warnings.warn("thewhisper_b200: fp32 operands are not supported; running bfloat16 operands with fp32 accumulation "
+                          "(pass torch_dtype=torch.float16 for the reference's fp16 mode)", stacklevel=2)
         self.tokenizer = tokenizer
         self.feature_extractor = feature_extractor
         self.config = model.config
@@ -78,7 +87,7 @@ class ASRPipeline:
             self.engine.close()
         self.engine = WhisperEngine(self._state_dict, self.dims, chunk_length_s=self.chunk_length_s, device=self.device,
                                     max_audios=capacity, max_beams=self.max_beams,
-                                    alignment_heads=self.settings.alignment_heads, weights=self._weights)
+                                    alignment_heads=self.settings.alignment_heads, weights=self._weights, dtype=self.engine_dtype)
         self._weights = self.engine.weights
         self._state_dict = None if self._weights is not None else self._state_dict
         self.capacity = capacity
