@@ -112,14 +112,19 @@ int bw_decode_reorder(bw_engine* e, const int32_t* parent_host, const int32_t* n
  * (:2945-3072) stays on the host (thewhisper_b200/beam.py). */
 int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_scores_host, int32_t* cand_tokens_host,
                         void* stream);
-/* word timestamps for audio a: n_tokens generated tokens starting at alignment row 0, num_frames valid encoder
- * frames (<= S); out_host [n_tokens + 1] seconds */
+/* word timestamps for sequence slot `audio` (= the audio index when decoding one sequence per audio): n_tokens generated tokens
+ * starting at alignment row 0, num_frames valid encoder frames (<= S); out_host [n_tokens + 1] seconds */
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, double time_precision,
                        float* out_host, void* stream);
 /* the same for n audios in one pass (4 kernel launches + one D2H whatever n is): audio[i], n_tokens[i], num_frames[i];
  * out_host [n][out_pitch] floats, out_pitch >= max n_tokens + 1 */
 int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
                              double time_precision, float* out_host, int32_t out_pitch, void* stream);
+/* beam search: alignment scores are kept per SEQUENCE slot (audio * G + beam); row t of item i is read from slot
+ * slot_map[i * map_pitch + t] -- the slot that was the returned sequence's ancestor at step t, i.e. what
+ * `_extract_token_timestamps` selects with `beam_indices` (TF/models/whisper/generation_whisper.py:265-301). */
+int bw_word_timestamps_gather(bw_engine* e, int32_t n, const int32_t* slot_map, int32_t map_pitch, const int32_t* n_tokens,
+                              const int32_t* num_frames, double time_precision, float* out_host, int32_t out_pitch, void* stream);
 
 /* ---- host-side post-processing (no CUDA) ---------------------------------------------------------------------- */
 /* Seam merge of overlapping chunks: the reference's patched `_find_longest_common_sequence`

@@ -62,6 +62,7 @@ class StubEngine:
         self._G = G
         self._plen = self._prompts.shape[1]
         self._seqs = [list(map(int, r)) for r in self._prompts]
+        self._slot_rows = []
 
     @torch.no_grad()
     def decode_beam_step(self, run_scores):
@@ -69,7 +70,14 @@ class StubEngine:
         A, G, o = self._A, self._G, self._opts
         ids = torch.tensor(self._seqs, dtype=torch.long)
         enc = self.enc[:A].repeat_interleave(G, dim=0)
-        out = self.model.model.decoder(input_ids=ids, encoder_hidden_states=enc)
+        want_align = bool(self.alignment_heads) and getattr(o, "record_alignment", False)
+        if want_align:
+            self.model.config._attn_implementation = "eager"
+        out = self.model.model.decoder(input_ids=ids, encoder_hidden_states=enc, output_attentions=want_align)
+        if want_align:  # cross-attention of the newest position of every SLOT at this step (the engine keeps one block per slot)
+            row = np.stack([np.stack([out.cross_attentions[l][q, h, -1].float().numpy() for l, h in self.alignment_heads]) for q in range(A * G)])
+            if len(self._seqs[0]) > self._plen:  # row 0 = the forward pass that consumed the first generated token
+                self._slot_rows.append(row)  # [Q, Ha, S]
         lg = self.model.proj_out(out.last_hidden_state[:, -1]).float()
         lp = torch.log_softmax(lg, dim=-1).numpy()
         K = 2 * G
@@ -152,6 +160,13 @@ class StubEngine:
         out = np.zeros((len(audios), int(max(n_tokens)) + 1), dtype=np.float32)
         for i, (a, t, f) in enumerate(zip(audios, n_tokens, num_frames)):
             out[i, : t + 1] = self.word_timestamps(a, t, f, time_precision)
+        return out
+
+    def word_timestamps_gather(self, slot_map, n_tokens, num_frames, time_precision: float = 0.02) -> np.ndarray:
+        out = np.zeros((len(n_tokens), int(max(n_tokens)) + 1), dtype=np.float32)
+        for i, (t, f) in enumerate(zip(n_tokens, num_frames)):
+            w = np.stack([self._slot_rows[r][int(slot_map[i][r])] for r in range(t)], axis=1)  # [Ha, T, S]
+            out[i, : t + 1] = whisper_ref.token_timestamps(w, f, time_precision)
         return out
 
     def word_timestamps(self, audio: int, n_tokens: int, num_frames: int, time_precision: float = 0.02) -> np.ndarray:

@@ -162,6 +162,8 @@ def golden_model(ASRPipeline, preset, tag, chunk_s, audio_s, n_tf=24, max_new=32
                            generate_kwargs=dict(gk))
         gk5 = dict(gk, num_beams=5)
         res["beam5"] = pipe(long_audio.copy(), chunk_length_s=chunk_s - 1, batch_size=4, generate_kwargs=gk5)
+        # word timestamps under beam search: cross-attention rows gathered along the winner's ancestry (beam_indices)
+        res["word_beam5"] = pipe(long_audio.copy(), chunk_length_s=chunk_s - 1, batch_size=4, return_timestamps="word", generate_kwargs=gk5)
         # the restated glue must reproduce the reference exactly
         model2 = S.make_hf_model(preset, seed=0, layer_gain=gain)
         pipe2 = hf_ref.make_ref_pipeline(model2, S.make_feature_extractor(chunk_s), tok, chunk_length_s=chunk_s,

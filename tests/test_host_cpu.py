@@ -190,6 +190,24 @@ def test_pipeline_host_logic_matches_reference(monkeypatch, mode):
     assert _same(norm, ref), (norm, ref)
 
 
+def test_pipeline_word_timestamps_under_beam_search_match_reference(monkeypatch):
+    """return_timestamps="word" with num_beams=5 (missing #4): the alignment rows of the returned sequence are gathered
+    along its ancestry (`beam_indices`, TF generation_whisper.py:265-301).  Host logic (beam bookkeeping incl. beam_indices, row map,
+    length rules) on the CPU stand-in against the REAL reference's output for the same audio."""
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, "model_tiny10.json")))
+    if "word_beam5" not in meta["pipeline"]:
+        pytest.skip("golden predates the word + beam case")
+    pipe = _stub_pipeline(monkeypatch, meta["preset"], meta["layer_gain"], meta["chunk_s"], batch_size=4)
+    audio = S.synth_audio(meta["audio_s"], seed=2000)
+    gk = {"num_beams": 5, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": 32}
+    out = pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=4, return_timestamps="word", generate_kwargs=dict(gk))
+    ref = meta["pipeline"]["word_beam5"]
+    norm = json.loads(json.dumps(out, default=lambda o: float(o)))
+    assert _same(norm, ref), (norm, ref)
+
+
 def test_oracle_replay_checker_on_stub(monkeypatch):
     """The tie-aware replay used by the GPU pipeline tests (tests/parity_utils.py) finds zero near ties when the engine
     is the fp32 CPU stand-in: recorder hooks, prompt/EOS bookkeeping and the logits rules line up with the oracle."""

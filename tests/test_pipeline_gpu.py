@@ -101,6 +101,31 @@ def test_pipeline_beam_search_matches_reference(cuda):
     _check_text(out["text"], meta["pipeline"]["beam5"]["text"], min_prefix=8, min_ratio=0.5)
 
 
+def test_pipeline_word_timestamps_under_beam_search(cuda):
+    """return_timestamps="word" with num_beams=5: alignment scores are kept per sequence slot on the device and the timestamp kernels
+    gather each step's row from the slot that was the winner's ancestor (bw_word_timestamps_gather).  The host logic is pinned
+    exactly against the real reference on the CPU stand-in (tests/test_host_cpu.py); here the CUDA path must reproduce the reference's
+    words on the common prefix with DTW times within a frame."""
+    from thewhisper_b200 import synthetic as S
+
+    meta, model, pipe = _pipe()
+    if "word_beam5" not in meta["pipeline"]:
+        pytest.skip("golden predates the word + beam case")
+    audio = S.synth_audio(meta["audio_s"], seed=2000)
+    out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, return_timestamps="word", generate_kwargs=dict(GK, num_beams=5))
+    ref = meta["pipeline"]["word_beam5"]
+    _check_text(out["text"], ref["text"], min_prefix=6, min_ratio=0.5)
+    got, want = json.loads(json.dumps(out["chunks"], default=float)), ref["chunks"]
+    n = 0
+    while n < min(len(got), len(want)) and got[n]["text"] == want[n]["text"]:
+        n += 1
+    assert n >= 6, (n, got[:8], want[:8])
+    close = sum(all((a is None and b is None) or (a is not None and b is not None and abs(a - b) <= 0.02 + 1e-6)
+                    for a, b in zip(g["timestamp"], r["timestamp"])) for g, r in zip(got[:n], want[:n]))
+    print(f"\n[word+beam] {n} common-prefix words, {close} with both times within one frame of the reference")
+    assert close >= 0.8 * n, (close, n)
+
+
 def test_pipeline_vs_live_oracle_small30(cuda):
     """30 s windows, 3-layer model, word timestamps, against the oracle run on the CPU in the same test.
     (1) rigorous and tie-aware: every decode call the pipeline made is replayed through the oracle by teacher forcing --

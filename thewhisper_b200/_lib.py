@@ -61,6 +61,7 @@ SYMBOLS = {
     "bw_decode_beam_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "bw_word_timestamps": (C.c_int, [_P, _I, _I, _I, C.c_double, _P, _P]),
     "bw_word_timestamps_batch": (C.c_int, [_P, _I, _P, _P, _P, C.c_double, _P, _I, _P]),
+    "bw_word_timestamps_gather": (C.c_int, [_P, _I, _P, _I, _P, _P, C.c_double, _P, _I, _P]),
     "bw_host_merge_overlapping": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
     "bw_op_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _I, _I, _I, _P]),
     "bw_op_gemm_splitk": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),

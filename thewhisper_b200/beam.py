@@ -23,8 +23,10 @@ def _topk_desc(values: np.ndarray, k: int) -> np.ndarray:
     return order[:, :k]
 
 
-def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, length_penalty: float = 1.0):
-    """prompts [A, plen].  Returns (generated ids per audio (best beam, cut before EOS), n_steps, eos_seen)."""
+def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, length_penalty: float = 1.0, return_beam_indices: bool = False):
+    """prompts [A, plen].  Returns (generated ids per audio (best beam, cut before EOS), n_steps, eos_seen) and, on request, the
+    `beam_indices` of the returned sequences as GenerationMixin._beam_search keeps them (TF generation/utils.py:2984-2997,3065-3070):
+    entry t = the global sequence slot (audio * G + beam) whose forward pass produced generated token t, -1 beyond the sequence."""
     plen = prompts.shape[1]
     V = eng.dims.vocab
     Tmax = eng.dims.max_target_positions
@@ -42,6 +44,8 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
     running_scores[:, 1:] = NEG
     beam_scores = np.full((A, G), NEG, dtype=np.float32)
     finished = np.zeros((A, G), dtype=bool)
+    running_bidx = np.full((A, G, Tmax), -1, dtype=np.int64)
+    bidx = running_bidx.copy()
     unsat = np.ones((A, 1), dtype=bool)
     top_mask = np.arange(K) < G
     cur_len = plen
@@ -61,12 +65,15 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
         top_tok = np.where(top_tok >= 0, top_tok, pad)
         top_seq = np.take_along_axis(running_seq, top_beam[:, :, None], 1).copy()  # [A, K, Tmax]
         top_seq[:, :, cur_len] = top_tok
+        top_bidx = np.take_along_axis(running_bidx, top_beam[:, :, None], 1).copy()
+        top_bidx[:, :, cur_len - plen] = top_beam + (np.arange(A) * G)[:, None]
         hits = (top_tok == opts.eos_token) | (cur_len + 1 >= max_length)
         # running beams of the next iteration
         run_lp = top_scores + hits.astype(np.float32) * NEG
         nxt = _topk_desc(run_lp, G)
         running_seq = np.take_along_axis(top_seq, nxt[:, :, None], 1)
         running_scores = np.take_along_axis(run_lp, nxt, 1)
+        running_bidx = np.take_along_axis(top_bidx, nxt[:, :, None], 1)
         parents = np.take_along_axis(top_beam, nxt, 1)
         next_tok = np.take_along_axis(top_tok, nxt, 1)
         # finished beams
@@ -77,8 +84,10 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
         m_scores = np.concatenate([beam_scores, lp], 1)
         m_seq = np.concatenate([sequences, top_seq], 1)
         m_fin = np.concatenate([finished, did_finish], 1)
+        m_bidx = np.concatenate([bidx, top_bidx], 1)
         sel = _topk_desc(m_scores, G)
         sequences = np.take_along_axis(m_seq, sel[:, :, None], 1)
+        bidx = np.take_along_axis(m_bidx, sel[:, :, None], 1)
         beam_scores = np.take_along_axis(m_scores, sel, 1)
         finished = np.take_along_axis(m_fin, sel, 1)
         cur_len += 1
@@ -97,4 +106,6 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
         cut = np.where(row == opts.eos_token)[0]
         eos_seen.append(len(cut) > 0)
         gen.append(row[: cut[0]] if len(cut) else row)
+    if return_beam_indices:
+        return gen, steps, eos_seen, bidx[:, 0, :]
     return gen, steps, eos_seen

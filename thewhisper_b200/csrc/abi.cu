@@ -104,6 +104,10 @@ int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, cons
                              double time_precision, float* out_host, int32_t out_pitch, void* stream) {
   BW_FWD(bw_word_timestamps_batch, e, n, audio, n_tokens, num_frames, time_precision, out_host, out_pitch, stream);
 }
+int bw_word_timestamps_gather(bw_engine* e, int32_t n, const int32_t* slot_map, int32_t map_pitch, const int32_t* n_tokens,
+                              const int32_t* num_frames, double time_precision, float* out_host, int32_t out_pitch, void* stream) {
+  BW_FWD(bw_word_timestamps_gather, e, n, slot_map, map_pitch, n_tokens, num_frames, time_precision, out_host, out_pitch, stream);
+}
 
 // ---- single ops: the bf16 build ------------------------------------------------------------------------------------------------
 int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,

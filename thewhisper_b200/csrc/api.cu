@@ -38,8 +38,8 @@ int g_pdl = 0;
 static int g_pdl_enabled = -1;  // BW_PDL (default on); cleared if a step with programmatic launches cannot be captured
 
 size_t word_timestamps_work_floats(int Ha, int Tcap, int S);  // timestamps.cu
-int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
-                                 double time_precision, float* work, float* out_dev);
+int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, const int* slot_map_dev,
+                                 int map_pitch, int n, int maxT, int maxNF, double time_precision, float* work, float* out_dev);
 
 namespace {
 
@@ -93,7 +93,7 @@ struct bw_engine {
   unsigned long long* sel_best = nullptr;
   float *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dq = nullptr, *dh = nullptr, *logits = nullptr, *part_o = nullptr,
         *part_ml = nullptr, *align = nullptr, *lse = nullptr, *ts_work = nullptr, *ts_out = nullptr;
-  int *reorder_tmp = nullptr, *cand_tokens = nullptr, *ts_items = nullptr;
+  int *reorder_tmp = nullptr, *cand_tokens = nullptr, *ts_items = nullptr, *ts_map = nullptr;
   float *run_scores = nullptr, *cand_scores = nullptr;
   size_t align_bytes = 0;
   // current decode session
@@ -683,7 +683,8 @@ int bw_engine_finalize(bw_engine* e) {
   }
   if (c.n_align_heads > 0) {
     BW_CHECK((int)e->align_pairs.size() == 2 * c.n_align_heads, "alignment heads not set");
-    if (dalloc(e, "align", &e->align, (size_t)A * c.n_align_heads * c.max_align_steps * S)) return -1;
+    if (dalloc(e, "align", &e->align, (size_t)Qm * c.n_align_heads * c.max_align_steps * S)) return -1;  // one block per sequence slot
+    if (dalloc(e, "ts_map", &e->ts_map, (size_t)A * c.max_align_steps)) return -1;
     if (dalloc(e, "ts_work", &e->ts_work, (size_t)A * word_timestamps_work_floats(c.n_align_heads, c.max_align_steps, S), false)) return -1;
     if (dalloc(e, "ts_out", &e->ts_out, (size_t)A * (c.max_align_steps + 8))) return -1;
     if (dalloc(e, "ts_items", &e->ts_items, (size_t)A * 3)) return -1;
@@ -860,32 +861,55 @@ int bw_decode_beam_step(bw_engine* e, const float* run_scores_host, float* cand_
   return 0;
 }
 
-int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
-                             double time_precision, float* out_host, int32_t out_pitch, void* stream) {
-  BW_CHECK(e && e->finalized && audio && n_tokens && num_frames && out_host, "bw_word_timestamps_batch: bad arguments");
+static int word_timestamps_impl(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* slot_map, int32_t map_pitch, const int32_t* n_tokens,
+                                const int32_t* num_frames, double time_precision, float* out_host, int32_t out_pitch, void* stream) {
+  BW_CHECK(e && e->finalized && (audio || slot_map) && n_tokens && num_frames && out_host, "bw_word_timestamps: bad arguments");
   BW_CHECK(e->cfg.n_align_heads > 0 && e->align, "bw_word_timestamps: engine built without alignment heads");
-  BW_CHECK(n >= 1 && n <= e->cfg.max_audios, "bw_word_timestamps_batch: n=%d outside 1..%d", n, e->cfg.max_audios);
-  const int Tcap = e->cfg.max_align_steps;
-  std::vector<int> items((size_t)n * 3);
+  BW_CHECK(n >= 1 && n <= e->cfg.max_audios, "bw_word_timestamps: n=%d outside 1..%d", n, e->cfg.max_audios);
+  const int Tcap = e->cfg.max_align_steps, Qm = e->cfg.max_audios * e->cfg.max_beams;
+  std::vector<int> items((size_t)n * 3), map;
   int maxT = 0, maxNF = 0;
   for (int i = 0; i < n; ++i) {
-    BW_CHECK(audio[i] >= 0 && audio[i] < e->cfg.max_audios, "bw_word_timestamps: audio index out of range");
     BW_CHECK(n_tokens[i] >= 1 && n_tokens[i] <= Tcap, "bw_word_timestamps: n_tokens=%d outside 1..%d", n_tokens[i], Tcap);
     BW_CHECK(num_frames[i] >= 1 && num_frames[i] <= e->S, "bw_word_timestamps: num_frames=%d outside 1..%d", num_frames[i], e->S);
-    BW_CHECK(out_pitch >= n_tokens[i] + 1, "bw_word_timestamps_batch: out_pitch=%d too small for %d tokens", out_pitch, n_tokens[i]);
-    items[3 * i] = audio[i]; items[3 * i + 1] = n_tokens[i]; items[3 * i + 2] = num_frames[i];
+    BW_CHECK(out_pitch >= n_tokens[i] + 1, "bw_word_timestamps: out_pitch=%d too small for %d tokens", out_pitch, n_tokens[i]);
+    if (audio) BW_CHECK(audio[i] >= 0 && audio[i] < Qm, "bw_word_timestamps: slot index out of range");
+    items[3 * i] = audio ? audio[i] : 0; items[3 * i + 1] = n_tokens[i]; items[3 * i + 2] = num_frames[i];
     maxT = n_tokens[i] > maxT ? n_tokens[i] : maxT;
     maxNF = num_frames[i] > maxNF ? num_frames[i] : maxNF;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (slot_map) {
+    BW_CHECK(map_pitch >= maxT, "bw_word_timestamps_gather: map_pitch=%d smaller than %d tokens", map_pitch, maxT);
+    map.assign((size_t)n * Tcap, 0);
+    for (int i = 0; i < n; ++i)
+      for (int t = 0; t < n_tokens[i]; ++t) {
+        const int sl = slot_map[(size_t)i * map_pitch + t];
+        BW_CHECK(sl >= 0 && sl < Qm, "bw_word_timestamps_gather: slot %d out of range", sl);
+        map[(size_t)i * Tcap + t] = sl;
+      }
+    BW_CUDA_OK(cudaMemcpyAsync(e->ts_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   BW_CUDA_OK(cudaMemcpyAsync(e->ts_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  if (int rc = word_timestamps_batch_device(st, e->align, e->cfg.n_align_heads, Tcap, e->S, e->ts_items, n, maxT, maxNF, time_precision,
-                                            e->ts_work, e->ts_out))
+  if (int rc = word_timestamps_batch_device(st, e->align, e->cfg.n_align_heads, Tcap, e->S, e->ts_items, slot_map ? e->ts_map : nullptr, Tcap, n, maxT,
+                                            maxNF, time_precision, e->ts_work, e->ts_out))
     return rc;
   BW_CUDA_OK(cudaMemcpy2DAsync(out_host, (size_t)out_pitch * sizeof(float), e->ts_out, (size_t)(Tcap + 8) * sizeof(float),
                                (size_t)(maxT + 1) * sizeof(float), n, cudaMemcpyDeviceToHost, st));
-  BW_CUDA_OK(cudaStreamSynchronize(st));  // `items` goes out of scope; the caller reads out_host
+  BW_CUDA_OK(cudaStreamSynchronize(st));  // the host staging vectors go out of scope; the caller reads out_host
   return 0;
+}
+
+int bw_word_timestamps_batch(bw_engine* e, int32_t n, const int32_t* audio, const int32_t* n_tokens, const int32_t* num_frames,
+                             double time_precision, float* out_host, int32_t out_pitch, void* stream) {
+  BW_CHECK(audio, "bw_word_timestamps_batch: null argument");
+  return word_timestamps_impl(e, n, audio, nullptr, 0, n_tokens, num_frames, time_precision, out_host, out_pitch, stream);
+}
+
+int bw_word_timestamps_gather(bw_engine* e, int32_t n, const int32_t* slot_map, int32_t map_pitch, const int32_t* n_tokens,
+                              const int32_t* num_frames, double time_precision, float* out_host, int32_t out_pitch, void* stream) {
+  BW_CHECK(slot_map, "bw_word_timestamps_gather: null argument");
+  return word_timestamps_impl(e, n, nullptr, slot_map, map_pitch, n_tokens, num_frames, time_precision, out_host, out_pitch, stream);
 }
 
 int bw_word_timestamps(bw_engine* e, int32_t audio, int32_t n_tokens, int32_t num_frames, double time_precision, float* out_host,

@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
   float* align_row = nullptr;
   if (slot >= 0 && a.align) {
     const int step = *a.pos - a.step_base;
-    if (step >= 0 && step < a.Tcap) align_row = a.align + (((long long)au * a.Ha + slot) * a.Tcap + step) * a.S + s0;
+    // one block of [Ha][Tcap][S] per SEQUENCE slot (au * G + g): beam search gathers a row per step from the slot that was the
+    // winner's ancestor at that step (bw_word_timestamps_gather)
+    if (step >= 0 && step < a.Tcap) align_row = a.align + (((long long)au * G * a.Ha + slot) * a.Tcap + step) * a.S + s0;
   }
   cp_async_wait_all();  // each thread reads back only the 16-byte pieces it copied itself
 #pragma unroll
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnArgs a) 
         d += __shfl_xor_sync(0xffffffffu, d, 4);
         if (sub == 0 && kk < n) {
           sc[g][kk] = d;
-          if (g == 0 && align_row) align_row[kk] = d;
+          if (align_row) align_row[(long long)g * a.Ha * a.Tcap * a.S + kk] = d;
         }
       }
     }
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnA
   float* align_base = nullptr;
   if (slot >= 0 && a.align) {
     const int step = *a.pos - a.step_base;
-    if (step >= 0 && step < a.Tcap) align_base = a.align + (((long long)au * a.Ha + slot) * a.Tcap + step) * S;
+    if (step >= 0 && step < a.Tcap) align_base = a.align + (((long long)au * G * a.Ha + slot) * a.Tcap + step) * S;
   }
   float m_run[GM], l_part[GM], o[GM][4];
 #pragma unroll
@@ -626,7 +628,11 @@ __global__ void __launch_bounds__(128) cross_attn_stream_kernel(const CrossAttnA
         }
       }
     }
-    if (align_base && valid) align_base[r0 + t] = sc[0];
+    if (align_base && valid) {
+#pragma unroll
+      for (int g = 0; g < GM; ++g)
+        if (g < G) align_base[(long long)g * a.Ha * a.Tcap * S + r0 + t] = sc[g];
+    }
 #pragma unroll
     for (int g = 0; g < GM; ++g) {
       if (g < G) {

@@ -19,7 +19,9 @@ namespace {
 // One descriptor per audio of a batch (blockIdx.z): which alignment block, how many generated tokens / valid frames.
 // Per-item scratch lives at work + z * work_stride (floats), results at out + z * out_stride.
 struct TsBatch {
-  const int* items;  // [n][3] device: audio index, T, NF
+  const int* items;     // [n][3] device: slot index of the alignment block, T, NF
+  const int* slot_map;  // optional [n][map_pitch]: row t of item i is read from slot slot_map[i * map_pitch + t] (beam search: the
+  int map_pitch;        // slot that was the returned sequence's ancestor at step t), null = the item's own slot for every row
   long long work_stride, out_stride, align_stride;
   int Ha, Tcap, S;
 };
@@ -42,8 +44,9 @@ __device__ __forceinline__ TsWork ts_work(float* work, const TsBatch& b, int ite
 __global__ void ts_softmax_kernel(const float* __restrict__ align, float* __restrict__ work, const TsBatch b) {
   __shared__ float red[32];
   const int t = blockIdx.x, ha = blockIdx.y, item = blockIdx.z;
-  const int audio = b.items[item * 3], T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2], Tcap = b.Tcap, S = b.S;
+  const int T = b.items[item * 3 + 1], NF = b.items[item * 3 + 2], Tcap = b.Tcap, S = b.S;
   if (t >= T) return;
+  const int audio = b.slot_map ? b.slot_map[item * b.map_pitch + t] : b.items[item * 3];
   const float* scores = align + (long long)audio * b.align_stride;
   float* probs = ts_work(work, b, item).probs;
   const float* row = scores + ((long long)ha * Tcap + t) * S;
@@ -200,10 +203,12 @@ size_t word_timestamps_work_floats(int Ha, int Tcap, int S) {
 }
 
 // n audios in one pass (4 launches whatever n is): items_dev [n][3] = (audio, T, NF); out_dev [n][Tcap + 8] seconds
-int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, int n, int maxT, int maxNF,
-                                 double time_precision, float* work, float* out_dev) {
+int word_timestamps_batch_device(cudaStream_t st, const float* align, int Ha, int Tcap, int S, const int* items_dev, const int* slot_map_dev,
+                                 int map_pitch, int n, int maxT, int maxNF, double time_precision, float* work, float* out_dev) {
   TsBatch b;
   b.items = items_dev;
+  b.slot_map = slot_map_dev;
+  b.map_pitch = map_pitch;
   b.work_stride = (long long)word_timestamps_work_floats(Ha, Tcap, S);
   b.out_stride = Tcap + 8;
   b.align_stride = (long long)Ha * Tcap * S;

@@ -368,6 +368,20 @@ class WhisperEngine:
                                                      pitch, self._stream()))
         return out
 
+    def word_timestamps_gather(self, slot_map: np.ndarray, n_tokens: Sequence[int], num_frames: Sequence[int],
+                               time_precision: float = 0.02) -> np.ndarray:
+        """Beam search: row t of item i comes from sequence slot slot_map[i, t] (the returned sequence's ancestor at step t)."""
+        sm = np.ascontiguousarray(slot_map, dtype=np.int32)
+        n = sm.shape[0]
+        nt = np.ascontiguousarray(n_tokens, dtype=np.int32)
+        nf = np.ascontiguousarray(num_frames, dtype=np.int32)
+        pitch = int(nt.max()) + 1
+        out = np.zeros((n, pitch), dtype=np.float32)
+        _lib.check(self.lib.bw_word_timestamps_gather(self.h, n, sm.ctypes.data_as(C.c_void_p), sm.shape[1], nt.ctypes.data_as(C.c_void_p),
+                                                      nf.ctypes.data_as(C.c_void_p), time_precision, out.ctypes.data_as(C.c_void_p),
+                                                      pitch, self._stream()))
+        return out
+
     def word_timestamps(self, audio: int, n_tokens: int, num_frames: int, time_precision: float = 0.02) -> np.ndarray:
         out = np.zeros(n_tokens + 1, dtype=np.float32)
         _lib.check(self.lib.bw_word_timestamps(self.h, audio, n_tokens, num_frames, time_precision,

@@ -9,7 +9,7 @@ What is covered (everything the reference's ASRPipeline / LocalWhisperBackend re
   * return_timestamps: WhisperTimeStamp rules on the device, segment split on timestamp pairs and the re-encode
     `seek` loop for unfinished segments (:785-903, :1976-2073)
   * return_token_timestamps: per-token times from the alignment heads (:241-381) with HF's row bookkeeping
-  * beam search (num_beams > 1) via thewhisper_b200.beam
+  * beam search (num_beams > 1) via thewhisper_b200.beam, incl. token timestamps along the winner's ancestry (beam_indices)
 Not covered (long-form only): temperature fallback, condition_on_prev_tokens, no-speech skipping.
 """
 from __future__ import annotations
@@ -139,9 +139,13 @@ class WhisperGenerator:
     # --------------------------------------------------------------------------------------------------------
     def _decode(self, prompts: np.ndarray, A: int, opts: DecodeOptions, max_new: int, num_beams: int):
         """-> (list of generated id arrays cut before EOS, n_steps HF would have run, eos_seen per row)"""
+        self._beam_indices = None
         if num_beams > 1:
             from .beam import beam_search
 
+            if opts.record_alignment:  # token timestamps need to know which slot produced each token of the winner
+                gen, steps, eos_seen, self._beam_indices = beam_search(self.eng, prompts, A, num_beams, opts, max_new, return_beam_indices=True)
+                return gen, steps, eos_seen
             return beam_search(self.eng, prompts, A, num_beams, opts, max_new)
         gen, toks, done = self.eng.greedy(prompts, A, opts, max_new)
         plen = prompts.shape[1]
@@ -155,6 +159,22 @@ class WhisperGenerator:
 
     def _token_timestamps(self, A: int, plen: int, n_steps: int, num_frames: np.ndarray) -> List[np.ndarray]:
         """HF layout: zeros for the prompt, one time per generated position, last one duplicated (:375-379)."""
+        bidx = getattr(self, "_beam_indices", None)
+        if bidx is not None:
+            # beam search (generation_whisper.py:265-301): the cross-attention row of step i comes from the sequence slot that was the
+            # returned sequence's ancestor at that step (`beam_indices`); the length is the longest returned sequence of the batch;
+            # steps beyond a shorter sequence's end (-1) read slot 0, exactly as the reference's masked_fill(…, 0) does
+            n_valid = int((bidx != -1).sum(-1).max())
+            T = n_valid - 1
+            out = [np.zeros(plen + n_valid, dtype=np.float32) for _ in range(A)]
+            if T >= 1 and A > 0:
+                Tc = min(T, self.eng.max_align_steps)
+                smap = np.where(bidx[:, 1:Tc + 1] >= 0, bidx[:, 1:Tc + 1], 0)  # row r <- the forward pass that consumed generated token r
+                nfs = [max(1, min(int(num_frames[a]) // 2, self.eng.S)) for a in range(A)]
+                jt = self.eng.word_timestamps_gather(smap, [Tc] * A, nfs, self.time_precision)
+                for a in range(A):
+                    out[a][plen:plen + Tc + 1] = jt[a, : Tc + 1]
+            return out
         T = n_steps - 1
         out = [np.zeros(plen + n_steps, dtype=np.float32) for _ in range(A)]
         if T >= 1 and A > 0:  # all audios of the batch in one pass of the four timestamp kernels
@@ -222,8 +242,6 @@ class WhisperGenerator:
             return_timestamps = True
             if not eng.alignment_heads:
                 raise ValueError("Model generation config has no `alignment_heads`, token-level timestamps not available.")
-            if num_beams > 1:
-                raise NotImplementedError("word timestamps with beam search are not supported by the B200 engine yet")
         if mel_f32 is None:
             raise ValueError("generate needs the fp32 features (engine.logmel(..., return_f32=True)) for the seek loop")
         if num_frames is None:
