@@ -179,13 +179,16 @@ def _ref_attn(qkv, B, S, H):
     return (w @ v).permute(0, 2, 1, 3).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tc"])
-@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 500, 2), (2, 333, 2), (1, 1500, 4)])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tc", "pingpong"])
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 500, 2), (2, 333, 2), (1, 1500, 4), (3, 750, 3), (2, 1000, 2), (1, 77, 1)])
 def test_attn_enc(cuda, impl, B, S, H):
     L, lib = _lib()
     g = torch.Generator(device="cpu").manual_seed(B * 100 + S + H)
     D = H * 64
-    qkv = (torch.randn(B * S, 3 * D, generator=g) * 1.5).to(torch.bfloat16).to(cuda)
+    qkv = torch.randn(B * S, 3 * D, generator=g) * 1.5
+    # rows whose scores grow along the key axis: the running maximum of the online softmax keeps rising (lazy-rescale path)
+    qkv[:, D:2 * D] *= torch.linspace(0.2, 3.0, B * S)[:, None]
+    qkv = qkv.to(torch.bfloat16).to(cuda)
     out = torch.zeros((B * S, D), dtype=torch.bfloat16, device=cuda)
     Spad = (S + 7) // 8 * 8
     vt = torch.zeros((B, H, 64, Spad), dtype=torch.bfloat16, device=cuda)

@@ -111,6 +111,7 @@ struct bw_engine {
   float* dpart = nullptr;
   int batch_min = 3;  // sequences from which a step runs on the tcgen05 path (BW_BATCH_MIN)
   bool gemm2 = true;  // encoder GEMMs on the CTA-pair kernel (BW_GEMM2=0: first-generation kernel only)
+  bool attn2 = true;  // encoder attention on the ping-pong kernel (BW_ATTN2=0: first-generation kernel)
   long long gemm2_min_rows = 1024;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
@@ -199,7 +200,7 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
       if (int rc = attn_enc_simt(st, e->qkv, e->ao, B, S, H)) return rc;
     } else {
       if (int rc = transpose_v(st, e->qkv, e->vt, B, S, e->Spad, H)) return rc;
-      if (int rc = attn_enc_tc(st, e->qkv, e->vt, e->ao, B, S, e->Spad, H)) return rc;
+      if (int rc = (e->attn2 ? attn_enc_tc2 : attn_enc_tc)(st, e->qkv, e->vt, e->ao, B, S, e->Spad, H)) return rc;
     }
     {
       GemmEpi ep = plainEpi(S, D);
@@ -537,6 +538,8 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
     if (bm) e->batch_min = atoi(bm);
     const char* g2 = getenv("BW_GEMM2");
     if (g2) e->gemm2 = g2[0] != '0';
+    const char* a2 = getenv("BW_ATTN2");
+    if (a2) e->attn2 = a2[0] != '0';
     const char* g2r = getenv("BW_GEMM2_MIN_ROWS");
     if (g2r) e->gemm2_min_rows = atoll(g2r);
   }
@@ -973,6 +976,7 @@ int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int3
   BW_CHECK(vt_scratch, "bw_op_attn_enc: vt_scratch required for the tcgen05 path");
   const int Spad = (S + 7) / 8 * 8;
   if (int rc = transpose_v(st, static_cast<const bf16*>(qkv), static_cast<bf16*>(vt_scratch), B, S, Spad, H)) return rc;
+  if (impl == 2) return attn_enc_tc2(st, static_cast<const bf16*>(qkv), static_cast<const bf16*>(vt_scratch), static_cast<bf16*>(out), B, S, Spad, H);
   return attn_enc_tc(st, static_cast<const bf16*>(qkv), static_cast<const bf16*>(vt_scratch), static_cast<bf16*>(out), B, S, Spad, H);
 }
 

@@ -237,6 +237,256 @@ attn_enc_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Second generation: two query tiles per CTA in ping-pong (the FlashAttention-4 schedule, restated in raw PTX).
+// Why (profiles/r2a_summary.md, r2bcd_summary.md: tensor pipe 14 %, sm__throughput 46 %): with ONE S buffer per CTA the tensor
+// pipe idles while the softmax warps exponentiate and vice versa, every key tile costs two dependent hand-overs, and the P.V
+// partial is read back from TMEM and folded into 64 registers per thread per tile.  Here
+//   * a CTA owns 256 query rows = two tiles A / B with their own S (128 TMEM columns each) and O (64 columns each) and their own
+//     softmax warpgroup (4 warps each): while group A exponentiates S_A(j), the tensor pipe runs QK_B(j) / PV_B(j-1), and K / V tiles
+//     are fetched once for 256 queries instead of once for 128;
+//   * O accumulates IN TMEM across key tiles (tcgen05.mma accumulate); a row's reference maximum is only raised when the tile maximum
+//     exceeds it by more than 2^8 (lazy rescaling: p <= 256 is harmless in bf16 / fp32), and then O is rescaled in place
+//     (tcgen05.ld -> multiply -> tcgen05.st); after the first tiles this almost never happens, so the per-tile O read-back is gone;
+//   * MMAs execute in issue order, so "S_g(j+1) is full" already implies "PV_g(j) is complete": no extra barrier for the rescale.
+// One CTA per SM: 192 KB smem (Q 2 x 16, K ring 3 x 16, V ring 3 x 16, P 2 x 32) and 384 of the 512 TMEM columns.
+// The exp unit bounds it: 16 MUFU.EX2 / clk / SM = 2048 clk per (256 queries x 128 keys) against 1024 clk of MMAs.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int KV_STAGES = 3;
+constexpr int ATT2_SMEM = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 256;
+constexpr float LAZY_TAU = 8.0f;  // log2 units: rescale O only when the tile maximum exceeds the reference by more than this
+
+__global__ void __launch_bounds__(320, 1)
+attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                   // [2][16 KB]
+  uint8_t* sK = sQ + 2 * Q_BYTES;                       // [KV_STAGES][16 KB]
+  uint8_t* sV = sK + KV_STAGES * K_BYTES;               // [KV_STAGES][16 KB]
+  uint8_t* sP = sV + KV_STAGES * V_BYTES;               // [2][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint64_t* q_full = bars + 0;                 // [2]
+  uint64_t* k_full = bars + 2;                 // [KV_STAGES]
+  uint64_t* v_full = bars + 2 + KV_STAGES;     // [KV_STAGES]
+  uint64_t* k_empty = bars + 2 + 2 * KV_STAGES;
+  uint64_t* v_empty = bars + 2 + 3 * KV_STAGES;
+  uint64_t* s_full = bars + 2 + 4 * KV_STAGES;      // [2]
+  uint64_t* p_full = s_full + 2;                    // [2]
+  uint64_t* o_final = p_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int NT = (p.S + TK - 1) / TK;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("[bw] attn_enc2: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_final[i], 1);
+    }
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVT);
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      const int row0 = b * p.S;
+      for (int g = 0; g < 2; ++g) {
+        mbar_arrive_expect_tx(&q_full[g], Q_BYTES);
+        tma_load_2d(sQ + g * Q_BYTES, &tmQK, &q_full[g], h * DH, row0 + q0 + g * TQ);
+      }
+      const int vrow = (b * p.H + h) * DH;
+      for (int j = 0; j < NT; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], K_BYTES);
+        tma_load_2d(sK + s * K_BYTES, &tmQK, &k_full[s], p.D + h * DH, row0 + j * TK);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], V_BYTES);
+        tma_load_2d(sV + s * V_BYTES, &tmVT, &v_full[s], j * TK, vrow);
+        tma_load_2d(sV + s * V_BYTES + V_BYTES / 2, &tmVT, &v_full[s], j * TK + 64, vrow);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, DH);
+      auto issue_qk = [&](int g, int stage) {
+        const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * Q_BYTES));
+        const uint64_t kd = umma_desc_sw128(smem_u32(sK + stage * K_BYTES));
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + g * TK, qd + 2 * k, kd + 2 * k, idesc_s, (uint32_t)(k != 0));
+      };
+      auto issue_pv = [&](int g, int stage, bool acc) {
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          const uint64_t pd = umma_desc_sw128(smem_u32(sP + g * P_BYTES + (k >> 2) * (P_BYTES / 2))) + 2 * (k & 3);
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV + stage * V_BYTES + (k >> 2) * (V_BYTES / 2))) + 2 * (k & 3);
+          umma_bf16(tmem_base + 256 + g * DH, pd, vd, idesc_o, (uint32_t)(acc || k != 0));
+        }
+      };
+      mbar_wait(&k_full[0], 0);
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&q_full[g], 0);
+        tc_fence_after();
+        issue_qk(g, 0);
+        umma_commit(&s_full[g]);
+      }
+      umma_commit(&k_empty[0]);  // K(0) is free once both QK(0) are done
+      for (int j = 0; j < NT; ++j) {
+        const int s = j % KV_STAGES, s2 = (j + 1) % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1, ph2 = ((j + 1) / KV_STAGES) & 1;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], j & 1);  // softmax g has consumed S_g(j), (rescaled O_g,) and published P_g(j)
+          if (g == 0) mbar_wait(&v_full[s], ph);
+          tc_fence_after();
+          issue_pv(g, s, j > 0);
+          if (j + 1 == NT) umma_commit(&o_final[g]);
+          if (g == 1) umma_commit(&v_empty[s]);
+          if (j + 1 < NT) {
+            if (g == 0) {
+              mbar_wait(&k_full[s2], ph2);
+              tc_fence_after();
+            }
+            issue_qk(g, s2);
+            umma_commit(&s_full[g]);
+            if (g == 1) umma_commit(&k_empty[s2]);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups: g = 0 (warps 0-3) rows [q0, q0+128), g = 1 (warps 4-7) rows [q0+128, q0+256) ----------------
+    const int g = warp >> 2, wq = warp & 3;
+    const int r = wq * 32 + lane;                       // row inside the tile = TMEM lane
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + g * TK;
+    const uint32_t tO = tmem_base + lane_sel + 256 + g * DH;
+    uint8_t* sPg = sP + g * P_BYTES;
+    float m_ref = -INFINITY, l = 0.f;  // m_ref in raw score units
+    for (int j = 0; j < NT; ++j) {
+      mbar_wait(&s_full[g], j & 1);   // S_g(j) is complete -- and so is PV_g(j-1): MMAs execute in issue order
+      tc_fence_after();
+      const int key0 = j * TK;
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_ld_wait();
+        const int kbase = key0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + i < p.S) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+      }
+      // lazy reference maximum: raise it only on the first tile or when this tile exceeds it by more than LAZY_TAU (log2 units)
+      float factor = 1.0f;
+      const bool raise = (j == 0) || ((tmax - m_ref) * p.scale_log2e > LAZY_TAU);
+      if (raise) {
+        factor = (j == 0) ? 0.f : exp2f((m_ref - tmax) * p.scale_log2e);
+        m_ref = tmax;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, raise)) {  // rescale this warp's 32 rows of O_g in place (PV_g(j-1) is complete)
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+          tmem_st_32x32(tO + c * 32, v);
+        }
+        tmem_st_wait();
+        l *= factor;
+      }
+      const float mb = m_ref * p.scale_log2e;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c * 32, v);
+        tmem_ld_wait();
+        const int kbase = key0 + c * 32;
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
+          pf[i] = (kbase + i < p.S) ? e : 0.f;
+          lsum += pf[i];
+        }
+        uint8_t* atom = sPg + (c >> 1) * (P_BYTES / 2) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
+          w.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
+          w.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
+          w.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) = w;
+        }
+      }
+      l += lsum;
+      fence_proxy_async_smem();  // P visible to the tensor core's async-proxy reads
+      tc_fence_before();         // our tcgen05.ld of S (and st of O) are complete before the issuer touches S / O again
+      mbar_arrive(&p_full[g]);
+    }
+    // ---- final O_g
+    mbar_wait(&o_final[g], 0);
+    tc_fence_after();
+    const int q = q0 + g * TQ + r;
+    const float inv = 1.0f / l;
+    bf16* op = p.out + ((long long)(b * p.S + q) * p.D + h * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tO + c * 32, v);
+      tmem_ld_wait();
+      if (q < p.S) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // CUDA-core sibling: one block per (query, head, batch); scores staged in smem.  Comparator / bring-up only.
 __global__ void attn_enc_simt_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int D, float scale) {
   extern __shared__ float sc[];  // S scores
@@ -313,6 +563,27 @@ int attn_enc_tc(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int
   p.out = out;
   dim3 grid((S + TQ - 1) / TQ, H, B);
   attn_enc_tc_kernel<<<grid, 192, ATT_SMEM, st>>>(tmQK, tmVT, p);
+  BW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int attn_enc_tc2(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int B, int S, int Spad, int H) {
+  const int D = H * DH;
+  BW_CHECK(Spad % 8 == 0 && Spad >= S, "attn_enc: Spad=%d must be >= S and a multiple of 8", Spad);
+  CUtensorMap tmQK, tmVT;
+  if (int rc = make_tmap_2d_bf16(&tmQK, qkv, (uint64_t)B * S, (uint64_t)3 * D, (uint64_t)3 * D * 2, TQ, DH)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmVT, vt, (uint64_t)B * H * DH, (uint64_t)Spad, (uint64_t)Spad * 2, DH, 64)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BW_CUDA_OK(cudaFuncSetAttribute(attn_enc_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.B = B; p.S = S; p.H = H; p.D = D;
+  p.scale_log2e = 0.125f * LOG2E;
+  p.out = out;
+  dim3 grid((S + 2 * TQ - 1) / (2 * TQ), H, B);
+  attn_enc_tc2_kernel<<<grid, 320, ATT2_SMEM, st>>>(tmQK, tmVT, p);
   BW_CUDA_OK(cudaGetLastError());
   return 0;
 }

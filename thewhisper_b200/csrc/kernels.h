@@ -74,6 +74,8 @@ int launch_gelu_bias(cudaStream_t st, const float* part, int nsplit, long long s
 // (zero beyond S), out: [B*S, D] bf16.  head_dim is 64 for every Whisper size.
 // ---------------------------------------------------------------------------------------------
 int attn_enc_tc(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int B, int S, int Spad, int H);
+// second generation: two query tiles per CTA in ping-pong, O accumulated in TMEM with lazy rescaling (same arguments)
+int attn_enc_tc2(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int B, int S, int Spad, int H);
 int attn_enc_simt(cudaStream_t st, const bf16* qkv, bf16* out, int B, int S, int H);
 int transpose_v(cudaStream_t st, const bf16* qkv, bf16* vt, int B, int S, int Spad, int H);
 

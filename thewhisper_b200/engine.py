@@ -322,6 +322,8 @@ class WhisperEngine:
         ct = np.empty((Q, K), dtype=np.int32)
         _lib.check(self.lib.bw_decode_beam_step(self.h, run.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p),
                                                 ct.ctypes.data_as(C.c_void_p), self._stream()))
+        self.stats["decode_steps"] += 1
+        self.stats["sequence_steps"] += Q
         return cs, ct
 
     def logits(self) -> torch.Tensor:

@@ -78,6 +78,18 @@ for sec in "$@"; do
       IFS=: read -r a g c <<< "$spec"
       BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 600 python tools/profile_decode.py 2>&1 | grep -E "decode step|encode|logmel|Error|error" | tee -a ${O}_steptime.log
     done ;;
+  driver)
+    # exactly what the driver runs at round end: the whole GPU suite in ONE process, then smoke()
+    timeout 1800 python -m pytest tests/ -x -q -m gpu > ${O}_driver_pytest.log 2>&1; tail -4 ${O}_driver_pytest.log
+    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee ${O}_smoke.log ;;
+  pdl)
+    for v in 1 0; do
+      for spec in "32:1:15" "64:1:30"; do
+        IFS=: read -r a g c <<< "$spec"
+        echo "BW_PDL=$v A=$a" | tee -a ${O}_pdl.log
+        BW_PDL=$v BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 600 python tools/profile_decode.py 2>&1 | grep -E "decode step|programmatic" | tee -a ${O}_pdl.log
+      done
+    done ;;
   *) echo "unknown section $sec" ;;
   esac
 done
