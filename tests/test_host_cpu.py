@@ -208,6 +208,17 @@ def test_pipeline_word_timestamps_under_beam_search_match_reference(monkeypatch)
     assert _same(norm, ref), (norm, ref)
 
 
+def test_overlong_max_new_tokens_raises_like_transformers(monkeypatch):
+    """TF generation_whisper.py:1920-1930: prompt + max_new_tokens beyond max_target_positions is a ValueError, not a silent clamp."""
+    from thewhisper_b200 import synthetic as S
+
+    meta = json.load(open(os.path.join(GOLD, "model_tiny10.json")))
+    pipe = _stub_pipeline(monkeypatch, meta["preset"], meta["layer_gain"], meta["chunk_s"], batch_size=1)
+    audio = S.synth_audio(5.0, seed=1)
+    with pytest.raises(ValueError, match="exceeds the `max_target_positions`"):
+        pipe(audio, generate_kwargs={"language": "en", "task": "transcribe", "max_new_tokens": 446})
+
+
 def test_oracle_replay_checker_on_stub(monkeypatch):
     """The tie-aware replay used by the GPU pipeline tests (tests/parity_utils.py) finds zero near ties when the engine
     is the fp32 CPU stand-in: recorder hooks, prompt/EOS bookkeeping and the logits rules line up with the oracle."""

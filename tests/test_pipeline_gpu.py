@@ -101,6 +101,23 @@ def test_pipeline_beam_search_matches_reference(cuda):
     _check_text(out["text"], meta["pipeline"]["beam5"]["text"], min_prefix=8, min_ratio=0.5)
 
 
+def test_pipeline_unusual_chunk_length(cuda):
+    """chunk_length_s = 12 (S = 600 encoder positions): the reference interpolates its positional table for any chunk length
+    (REF asr_pipeline.py:15-27); the engine does the same table and its kernels take any S.  Tie-aware replay through the oracle."""
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+
+    meta, model, pipe = _pipe(chunk_s=12, batch_size=2)
+    rec = _DecodeRecorder(pipe)
+    audio = S.synth_audio(20.0, seed=2100)
+    out = pipe(audio.copy(), chunk_length_s=11, batch_size=2, generate_kwargs=dict(GK))
+    assert isinstance(out["text"], str) and len(out["text"].split()) >= 3
+    om = S.make_hf_model(meta["preset"], seed=0, layer_gain=meta["layer_gain"])
+    hf_ref.interpolate_positions(om, 12)
+    near = _assert_oracle_greedy(rec.records, om, max_near_ties=4)
+    print(f"\n[chunk 12 s] {sum(len(g) for r in rec.records for g in r['gen'])} tokens replayed through the oracle, {near} near ties")
+
+
 def test_pipeline_word_timestamps_under_beam_search(cuda):
     """return_timestamps="word" with num_beams=5: alignment scores are kept per sequence slot on the device and the timestamp kernels
     gather each step's row from the slot that was the winner's ancestor (bw_word_timestamps_gather).  The host logic is pinned

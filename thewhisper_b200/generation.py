@@ -252,10 +252,17 @@ class WhisperGenerator:
         prompts_all = self.init_tokens(B, language, task, return_timestamps)
         plen = prompts_all.shape[1]
         max_new = max_new_tokens if max_new_tokens is not None else st.max_length - plen
-        if max_new + plen > eng.dims.max_target_positions:
-            if max_new_tokens is not None and max_new_tokens + plen > eng.dims.max_target_positions and plen >= eng.dims.max_target_positions:
-                raise ValueError("decoder prompt longer than max_target_positions")
-            max_new = eng.dims.max_target_positions - plen
+        mtp = eng.dims.max_target_positions
+        if (max_new_tokens or 0) + plen > mtp:  # same check, same message as TF generation_whisper.py:1920-1930
+            raise ValueError(
+                f"The length of `decoder_input_ids`, including special start tokens, prompt tokens, and previous tokens, is {plen}, "
+                f" and `max_new_tokens` is {max_new_tokens or 0}. Thus, the combined length of "
+                f"`decoder_input_ids` and `max_new_tokens` is: {(max_new_tokens or 0) + plen}. This exceeds the "
+                f"`max_target_positions` of the Whisper model: {mtp}. "
+                "You should either reduce the length of your prompt, or reduce the value of `max_new_tokens`, "
+                f"so that their combined length is less than {mtp}.")
+        if max_new + plen > mtp:  # (only the max_length default can get here)
+            max_new = mtp - plen
         opts = self._opts(return_timestamps, return_token_timestamps, extra_suppress)
 
         seek = np.zeros(B, dtype=np.int64)

@@ -50,8 +50,11 @@ class ASRPipeline:
                 raise ValueError("feature_extractor must be provided when passing a model instance")
             if tokenizer is None:
                 raise ValueError("tokenizer must be provided when passing a model instance")
-        if chunk_length_s not in (10, 15, 20, 30):
-            raise ValueError(f"chunk_length_s={chunk_length_s} is not supported (10, 15, 20 or 30)")
+        # the reference interpolates the positional table for ANY chunk length (REF asr_pipeline.py:15-27, :91-92); the kernels need a
+        # whole number of encoder positions S = 1500 * c / 30 with 50 <= S <= 1500
+        if not (1 <= chunk_length_s <= 30) or abs(1500 * chunk_length_s / 30 - round(1500 * chunk_length_s / 30)) > 1e-9:
+            raise ValueError(f"chunk_length_s={chunk_length_s} is not supported: it must lie in 1..30 s and give a whole number of encoder "
+                             f"positions (a multiple of 0.02 s)")
         self.chunk_length_s = chunk_length_s
         # torch_dtype picks the engine's 16-bit element type: float16 as the reference's streaming / benchmark paths pass it, else
         # bfloat16 (None / float32 = the reference's default fp32 model: the engine has no fp32-operand mode and says so once)
