@@ -15,6 +15,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from tests.conftest import GOLD
 from tests.parity_utils import DecodeRecorder as _DecodeRecorder, assert_oracle_greedy as _assert_oracle_greedy
@@ -95,7 +96,10 @@ def test_pipeline_word_timestamps_match_reference(cuda):
 def test_pipeline_beam_search_matches_reference(cuda):
     from thewhisper_b200 import synthetic as S
 
-    meta, model, pipe = _pipe()
+    # beam search on a random checkpoint is chaotic (one flipped candidate changes the rest of a window): run it on the float16 build of
+    # the engine, whose logits are ~10x closer to the fp32 reference than bf16's (profiles/r2bcd_summary.md) -- the reference's own
+    # streaming / benchmark dtype.  Per-step candidate parity is pinned rigorously in test_model_gpu.py::test_beam_candidates_*.
+    meta, model, pipe = _pipe(torch_dtype=torch.float16)
     audio = S.synth_audio(meta["audio_s"], seed=2000)
     out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, generate_kwargs=dict(GK, num_beams=5))
     _check_text(out["text"], meta["pipeline"]["beam5"]["text"], min_prefix=8, min_ratio=0.5)
@@ -125,7 +129,7 @@ def test_pipeline_word_timestamps_under_beam_search(cuda):
     words on the common prefix with DTW times within a frame."""
     from thewhisper_b200 import synthetic as S
 
-    meta, model, pipe = _pipe()
+    meta, model, pipe = _pipe(torch_dtype=torch.float16)  # (float16 build: see test_pipeline_beam_search_matches_reference)
     if "word_beam5" not in meta["pipeline"]:
         pytest.skip("golden predates the word + beam case")
     audio = S.synth_audio(meta["audio_s"], seed=2000)

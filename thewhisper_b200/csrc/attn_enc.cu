@@ -392,22 +392,28 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       mbar_wait(&s_full[g], j & 1);   // S_g(j) is complete -- and so is PV_g(j-1): MMAs execute in issue order
       tc_fence_after();
       const int key0 = j * TK;
+      const bool ragged = key0 + TK > p.S;  // only the last key tile has keys beyond S: the mask costs 2 of ~6 instructions per score
       float tmax = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tS + c * 32, v);
         tmem_ld_wait();
-        const int kbase = key0 + c * 32;
+        if (!ragged) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + i < p.S) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+        } else {
+          const int kbase = key0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + i < p.S) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+        }
       }
       // lazy reference maximum: raise it only on the first tile or when this tile exceeds it by more than LAZY_TAU (log2 units)
       float factor = 1.0f;
       const bool raise = (j == 0) || ((tmax - m_ref) * p.scale_log2e > LAZY_TAU);
       if (raise) {
-        factor = (j == 0) ? 0.f : exp2f((m_ref - tmax) * p.scale_log2e);
+        factor = (j == 0) ? 0.f : ex2_approx((m_ref - tmax) * p.scale_log2e);
         m_ref = tmax;
       }
       if (j > 0 && __any_sync(0xffffffffu, raise)) {  // rescale this warp's 32 rows of O_g in place (PV_g(j-1) is complete)
@@ -430,13 +436,21 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         uint32_t v[32];
         tmem_ld_32x32(tS + c * 32, v);
         tmem_ld_wait();
-        const int kbase = key0 + c * 32;
         float pf[32];
+        if (!ragged) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
-          pf[i] = (kbase + i < p.S) ? e : 0.f;
-          lsum += pf[i];
+          for (int i = 0; i < 32; ++i) {
+            pf[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
+            lsum += pf[i];
+          }
+        } else {
+          const int kbase = key0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
+            pf[i] = (kbase + i < p.S) ? e : 0.f;
+            lsum += pf[i];
+          }
         }
         uint8_t* atom = sPg + (c >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll

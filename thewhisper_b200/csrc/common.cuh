@@ -72,6 +72,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 2^x on the SFU, one instruction (MUFU.EX2; flush-to-zero): exp2f() wraps the same instruction in denormal-range fix-ups
+// (FSETP + 2 FMUL) that the softmax kernels do not need -- their arguments are <= 8 and underflow to 0 is what they want
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact (erf) GELU, as torch.nn.functional.gelu(approximate="none")
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
