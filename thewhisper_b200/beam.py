@@ -37,6 +37,9 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
     eng.decode_run(plen - 1)  # teacher-forced prompt positions
 
     pad = opts.pad_token
+    # (the bookkeeping arrays are as long as this decode can get, not max_target_positions: every step gathers and concatenates
+    # them -- at 64 audios x 5 beams that is the host's share of a step)
+    Tmax = max_length
     running_seq = np.full((A, G, Tmax), pad, dtype=np.int64)
     running_seq[:, :, :plen] = prompts[:, None, :]
     sequences = running_seq.copy()

@@ -393,21 +393,37 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       tc_fence_after();
       const int key0 = j * TK;
       const bool ragged = key0 + TK > p.S;  // only the last key tile has keys beyond S: the mask costs 2 of ~6 instructions per score
+      // Both passes keep the NEXT 32-column TMEM load in flight while the current one is processed, and fold through four independent
+      // accumulators: ncu of the first cut of this kernel showed 30 % long-scoreboard (tcgen05.ld -> wait -> use, eight times per
+      // tile) and 25 % fixed-latency stalls (32-deep dependent FMNMX / FADD chains) with only two softmax warps per scheduler.
       float tmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
+      {
+        uint32_t va[32], vb[32];
+        float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+        tmem_ld_32x32(tS, va);
         tmem_ld_wait();
-        if (!ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-        } else {
-          const int kbase = key0 + c * 32;
+        for (int c = 0; c < TK / 32; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < TK / 32) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
+          if (!ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + i < p.S) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4) {
+              t0 = fmaxf(t0, __uint_as_float(cur[i]));
+              t1 = fmaxf(t1, __uint_as_float(cur[i + 1]));
+              t2 = fmaxf(t2, __uint_as_float(cur[i + 2]));
+              t3 = fmaxf(t3, __uint_as_float(cur[i + 3]));
+            }
+          } else {
+            const int kbase = key0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + i < p.S) t0 = fmaxf(t0, __uint_as_float(cur[i]));
+          }
+          if (c + 1 < TK / 32) tmem_ld_wait();
         }
+        tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
       }
       // lazy reference maximum: raise it only on the first tile or when this tile exceeds it by more than LAZY_TAU (log2 units)
       float factor = 1.0f;
@@ -431,38 +447,49 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       }
       const float mb = m_ref * p.scale_log2e;
       float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
+      {
+        uint32_t va[32], vb[32];
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        tmem_ld_32x32(tS, va);
         tmem_ld_wait();
-        float pf[32];
-        if (!ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pf[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
-            lsum += pf[i];
+        for (int c = 0; c < TK / 32; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < TK / 32) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
+          float pf[32];
+          if (!ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              pf[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2e, -mb));
+              pf[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2e, -mb));
+              pf[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2e, -mb));
+              pf[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2e, -mb));
+              l0 += pf[i]; l1 += pf[i + 1]; l2 += pf[i + 2]; l3 += pf[i + 3];
+            }
+          } else {
+            const int kbase = key0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2e, -mb));
+              pf[i] = (kbase + i < p.S) ? e : 0.f;
+              l0 += pf[i];
+            }
           }
-        } else {
-          const int kbase = key0 + c * 32;
+          uint8_t* atom = sPg + (c >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mb));
-            pf[i] = (kbase + i < p.S) ? e : 0.f;
-            lsum += pf[i];
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
+            w.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
+            w.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
+            w.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
+            const int chunk = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) = w;
           }
+          if (c + 1 < TK / 32) tmem_ld_wait();
         }
-        uint8_t* atom = sPg + (c >> 1) * (P_BYTES / 2) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
-          w.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
-          w.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
-          w.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) = w;
-        }
+        lsum = (l0 + l1) + (l2 + l3);
       }
       l += lsum;
       fence_proxy_async_smem();  // P visible to the tensor core's async-proxy reads
