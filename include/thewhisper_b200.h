@@ -152,7 +152,9 @@ int bw_op_gelu_bias(const float* partials, int32_t nsplit, const float* bias, vo
 /* x[q] += bias + sum_s partials[s][q] (s ascending: deterministic), y[q] = LayerNorm(x[q]) as bf16 (y may be NULL). */
 int bw_op_resid_ln(float* x, const float* partials, int32_t nsplit, const float* bias, const float* ln_g, const float* ln_b, void* y_bf16,
                    int32_t Q, int32_t D, void* stream);
-/* qkv [B*S, 3D] bf16 -> out [B*S, D] bf16; vt_scratch [B, H, 64, Spad] bf16 (Spad = S rounded up to 8) */
+/* qkv [B*S, 3D] bf16 -> out [B*S, D] bf16; vt_scratch [B, H, 64, Spad] bf16 (Spad = S rounded up to 8).
+   impl 0 = tcgen05 (one query tile per CTA), 1 = CUDA-core comparator, 2 = tcgen05 ping-pong (two query tiles per CTA, O in TMEM),
+   3 = ping-pong reading V tiles from the qkv rows as an MN-major operand (vt_scratch unused). */
 int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int32_t S, int32_t H, int32_t impl, void* stream);
 int bw_op_layernorm(const float* x, const float* g, const float* b, void* out, int32_t out_is_f32, int32_t rows, int32_t D,
                     void* stream);

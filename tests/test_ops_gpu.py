@@ -147,29 +147,59 @@ def test_gemm_dec(cuda, Q, N, K):
         assert (h.float() - hr).abs().max().item() <= 1e-2 * max(1.0, hr.abs().max().item())
 
 
-@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tc", "pair"])
-def test_gemm_epilogues(cuda, impl):
+@pytest.mark.parametrize("impl,N,fbn", [(1, 640, 0), (0, 640, 0), (2, 640, 0), (2, 768, 0), (2, 640, 1128), (2, 768, 1256)],
+                         ids=["simt", "tc", "pair128", "pair256", "pair128-generic", "pair256-generic"])
+def test_gemm_epilogues(cuda, impl, N, fbn):
+    """bias / alpha / GELU / fp32 residual / 16-bit or fp32 output.  The CTA-pair kernel has one specialised epilogue per combination the
+    encoder uses (GELU -> 16 bit, residual -> fp32, plain -> 16 bit) and a generic one (force_bn = 1000 + bn selects it for all)."""
     g = torch.Generator(device="cpu").manual_seed(3)
-    M, N, K = 300, 640, 256
+    M, K = 300, 256
     A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
     W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).to(cuda)
     bias = torch.randn(N, generator=g).to(cuda)
     res = torch.randn(M, N, generator=g).to(cuda)
-    out = _gemm(A, W, bias=bias, alpha=0.125, act=0, residual=None, impl=impl)
+    out = _gemm(A, W, bias=bias, alpha=0.125, act=0, residual=None, impl=impl, force_bn=fbn)
     assert (out - _ref_gemm(A, W, bias, 0.125)).abs().max().item() < 2e-3
-    out = _gemm(A, W, bias=bias, act=1, impl=impl)
+    out = _gemm(A, W, bias=bias, act=1, impl=impl, force_bn=fbn)
     assert (out - _ref_gemm(A, W, bias, 1.0, 1)).abs().max().item() < 2e-3
-    out = _gemm(A, W, bias=bias, residual=res, impl=impl)
+    out = _gemm(A, W, bias=bias, residual=res, impl=impl, force_bn=fbn)
     assert (out - _ref_gemm(A, W, bias, 1.0, 0, res)).abs().max().item() < 2e-3
-    outb = _gemm(A, W, bias=bias, act=1, out_f32=False, impl=impl)
+    outb = _gemm(A, W, bias=bias, act=1, out_f32=False, impl=impl, force_bn=fbn)
     ref = _ref_gemm(A, W, bias, 1.0, 1)
     assert (outb.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())  # one bf16 rounding
+    outp = _gemm(A, W, bias=bias, out_f32=False, impl=impl, force_bn=fbn)
+    ref = _ref_gemm(A, W, bias)
+    assert (outp.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    outp = _gemm(A, W, out_f32=False, impl=impl, force_bn=fbn)  # no bias (the cross-attention K projection)
+    ref = _ref_gemm(A, W)
+    assert (outp.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
     # in-place residual (x += A W^T + b), as the encoder layers use it
     x = res.clone()
     L, lib = _lib()
-    L.check(lib.bw_op_gemm(_ptr(A), _ptr(W), M, N, K, _ptr(bias), 1.0, 0, _ptr(x), _ptr(x), 1, impl, 0, _stream()))
+    L.check(lib.bw_op_gemm(_ptr(A), _ptr(W), M, N, K, _ptr(bias), 1.0, 0, _ptr(x), _ptr(x), 1, impl, fbn, _stream()))
     torch.cuda.synchronize()
     assert (x - _ref_gemm(A, W, bias, 1.0, 0, res)).abs().max().item() < 2e-3
+
+
+def test_gemm_pair_gelu_matches_erf(cuda):
+    """The CTA-pair epilogue's GELU (Abramowitz-Stegun erfc: 2 MUFU + 12 fp32 operations) against the erf GELU in float64 on a fine grid
+    over [-9, 9]: x = hi + lo (two exact bf16 products accumulated in fp32) is steered through the accumulator, fp32 output."""
+    M, N, K = 128, 16384, 64
+    xs = torch.linspace(-9.0, 9.0, N)
+    hi = xs.to(torch.bfloat16)
+    lo = (xs - hi.float()).to(torch.bfloat16)
+    A = torch.zeros(M, K)
+    A[:, 0] = 1.0
+    A[:, 1] = 1.0
+    W = torch.zeros(N, K)
+    W[:, 0] = hi.float()
+    W[:, 1] = lo.float()
+    y = _gemm(A.to(torch.bfloat16).to(cuda), W.to(torch.bfloat16).to(cuda), act=1, impl=2)
+    x = hi.float() + lo.float()
+    ref = torch.nn.functional.gelu(x.double()).to(cuda)
+    err = (y.double() - ref[None, :]).abs().max().item()
+    assert err < 2e-6, err
+    assert torch.equal(y[0], y[M - 1])
 
 
 def _ref_attn(qkv, B, S, H):
@@ -179,7 +209,7 @@ def _ref_attn(qkv, B, S, H):
     return (w @ v).permute(0, 2, 1, 3).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tc", "pingpong"])
+@pytest.mark.parametrize("impl", [1, 0, 2, 3], ids=["simt", "tc", "pingpong", "pingpong-vdirect"])
 @pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 500, 2), (2, 333, 2), (1, 1500, 4), (3, 750, 3), (2, 1000, 2), (1, 77, 1)])
 def test_attn_enc(cuda, impl, B, S, H):
     L, lib = _lib()

@@ -112,7 +112,12 @@ struct bw_engine {
   int batch_min = 3;  // sequences from which a step runs on the tcgen05 path (BW_BATCH_MIN)
   bool gemm2 = true;  // encoder GEMMs on the CTA-pair kernel (BW_GEMM2=0: first-generation kernel only)
   bool attn2 = true;  // encoder attention on the ping-pong kernel (BW_ATTN2=0: first-generation kernel)
+  bool attn_vdirect = true;   // ... reading V tiles from the qkv rows (MN-major operand) instead of a transposed copy (BW_ATTN_VDIRECT=0: transposed copy)
   long long gemm2_min_rows = 1024;
+  bool enc_graph = false;  // BW_ENC_GRAPH=1: the encoder pass of a batch size runs as one CUDA graph from its second call on
+  bool enc_pdl = false;    // BW_ENC_PDL=1: ... and its kernels are chained by programmatic dependent launch
+  std::map<int, cudaGraphExec_t> enc_graphs;
+  std::map<int, int> enc_calls;
   int num_sms = 148;
   unsigned* mega_bar = nullptr;
   long long* mega_trace = nullptr;
@@ -199,8 +204,12 @@ int encode_impl(bw_engine* e, int B, cudaStream_t st) {
     if (e->simt) {
       if (int rc = attn_enc_simt(st, e->qkv, e->ao, B, S, H)) return rc;
     } else {
-      if (int rc = transpose_v(st, e->qkv, e->vt, B, S, e->Spad, H)) return rc;
-      if (int rc = (e->attn2 ? attn_enc_tc2 : attn_enc_tc)(st, e->qkv, e->vt, e->ao, B, S, e->Spad, H)) return rc;
+      if (e->attn2 && e->attn_vdirect) {  // V tiles straight from the qkv rows (MN-major tcgen05 operand): no transposed copy
+        if (int rc = attn_enc_tc2(st, e->qkv, nullptr, e->ao, B, S, e->Spad, H)) return rc;
+      } else {
+        if (int rc = transpose_v(st, e->qkv, e->vt, B, S, e->Spad, H)) return rc;
+        if (int rc = (e->attn2 ? attn_enc_tc2 : attn_enc_tc)(st, e->qkv, e->vt, e->ao, B, S, e->Spad, H)) return rc;
+      }
     }
     {
       GemmEpi ep = plainEpi(S, D);
@@ -540,6 +549,12 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
     if (g2) e->gemm2 = g2[0] != '0';
     const char* a2 = getenv("BW_ATTN2");
     if (a2) e->attn2 = a2[0] != '0';
+    const char* eg = getenv("BW_ENC_GRAPH");
+    if (eg) e->enc_graph = eg[0] != '0';
+    const char* ep = getenv("BW_ENC_PDL");
+    if (ep) e->enc_pdl = ep[0] != '0';
+    const char* avd = getenv("BW_ATTN_VDIRECT");
+    if (avd) e->attn_vdirect = avd[0] != '0';
     const char* g2r = getenv("BW_GEMM2_MIN_ROWS");
     if (g2r) e->gemm2_min_rows = atoll(g2r);
   }
@@ -565,6 +580,7 @@ int bw_engine_create(const bw_config* cfg, bw_engine** out) {
 void bw_engine_destroy(bw_engine* e) {
   if (!e) return;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : e->enc_graphs) cudaGraphExecDestroy(kv.second);
   for (auto& kv : e->buffers) cudaFree(kv.second.first);
   logmel_plan_destroy(e->mel_plan);
   delete e;
@@ -721,10 +737,59 @@ int bw_set_mel(bw_engine* e, const float* mel, int32_t B, void* stream) {
   return 0;
 }
 
+// The encoder pass: ~300 kernels (7 per layer + 64 cross-K/V projections).  At B = 1 they are 5-30 us each and the host's launch cost
+// (two cuTensorMapEncode + cudaLaunchKernelEx per GEMM) and the gaps between them are a third of the pass, so from the second call
+// with a given batch size on the pass is replayed as ONE CUDA graph whose kernel nodes are chained by programmatic dependent launch
+// (the first call runs on the stream: it also sets the kernels' function attributes, which must not happen under capture).
+static int encode_pdl(bw_engine* e, int B, cudaStream_t st) {
+  if (!e->enc_pdl) return encode_impl(e, B, st);
+  if (g_pdl_enabled < 0) {
+    const char* ev = getenv("BW_PDL");
+    g_pdl_enabled = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  g_pdl = g_pdl_enabled;
+  const int rc = encode_impl(e, B, st);
+  g_pdl = 0;
+  return rc;
+}
+
 int bw_encode(bw_engine* e, int32_t B, void* stream) {
   BW_CHECK(e && e->finalized, "bw_encode: engine not finalized");
   BW_CHECK(B >= 1 && B <= e->cfg.max_audios, "bw_encode: B=%d outside 1..%d", B, e->cfg.max_audios);
-  return encode_impl(e, B, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (e->no_graph || !e->enc_graph || e->simt) return encode_pdl(e, B, st);
+  auto it = e->enc_graphs.find(B);
+  if (it == e->enc_graphs.end()) {
+    if (e->enc_calls[B]++ == 0) return encode_pdl(e, B, st);
+    cudaStream_t cs;
+    BW_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    for (int attempt = 0; attempt < 2 && !exec; ++attempt) {
+      BW_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int rc = encode_pdl(e, B, cs);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      graph = nullptr;
+      if (rc == 0 && ce == cudaSuccess) break;
+      exec = nullptr;
+      cudaGetLastError();
+      if (attempt == 0 && g_pdl_enabled == 1) {
+        g_pdl_enabled = 0;  // a driver that cannot capture programmatic launches: plain edges
+        continue;
+      }
+      break;
+    }
+    cudaStreamDestroy(cs);
+    if (!exec) {  // no graph on this driver: stream launches from now on
+      e->enc_graph = false;
+      return encode_pdl(e, B, st);
+    }
+    it = e->enc_graphs.emplace(B, exec).first;
+  }
+  BW_CUDA_OK(cudaGraphLaunch(it->second, st));
+  return 0;
 }
 
 int bw_decode_begin(bw_engine* e, int32_t A, int32_t G, const int32_t* prompt, int32_t plen, const bw_decode_opts* opts, void* stream) {
@@ -975,6 +1040,7 @@ int bw_op_attn_enc(const void* qkv, void* vt_scratch, void* out, int32_t B, int3
   if (impl == 1) return attn_enc_simt(st, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, S, H);
   BW_CHECK(vt_scratch, "bw_op_attn_enc: vt_scratch required for the tcgen05 path");
   const int Spad = (S + 7) / 8 * 8;
+  if (impl == 3) return attn_enc_tc2(st, static_cast<const bf16*>(qkv), nullptr, static_cast<bf16*>(out), B, S, Spad, H);
   if (int rc = transpose_v(st, static_cast<const bf16*>(qkv), static_cast<bf16*>(vt_scratch), B, S, Spad, H)) return rc;
   if (impl == 2) return attn_enc_tc2(st, static_cast<const bf16*>(qkv), static_cast<const bf16*>(vt_scratch), static_cast<bf16*>(out), B, S, Spad, H);
   return attn_enc_tc(st, static_cast<const bf16*>(qkv), static_cast<const bf16*>(vt_scratch), static_cast<bf16*>(out), B, S, Spad, H);

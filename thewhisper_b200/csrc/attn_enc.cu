@@ -12,6 +12,8 @@
 //   warp  5    TMEM allocator + MMA issuer: S = Q K^T (4 x tcgen05.mma, N=128), O_j = P V (8 x, N=64)
 // 112 KB smem and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's exp phase overlaps the other's MMAs.
 // Keys beyond S (tile overrun into the next row block / TMA zero fill) are masked to -inf before the max.
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace BW_NS {
@@ -31,6 +33,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct AttnParams {
   int B, S, H, D;
   float scale_log2e;  // dh^-1/2 * log2(e)
+  int v_direct = 0;   // ping-pong kernel: V tiles come straight from the qkv rows (MN-major B operand), no transposed copy
   bf16* out;
 };
 
@@ -249,7 +252,9 @@ attn_enc_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_consta
 //   * O accumulates IN TMEM across key tiles (tcgen05.mma accumulate); a row's reference maximum is only raised when the tile maximum
 //     exceeds it by more than 2^8 (lazy rescaling: p <= 256 is harmless in bf16 / fp32), and then O is rescaled in place
 //     (tcgen05.ld -> multiply -> tcgen05.st); after the first tiles this almost never happens, so the per-tile O read-back is gone;
-//   * MMAs execute in issue order, so "S_g(j+1) is full" already implies "PV_g(j) is complete": no extra barrier for the rescale.
+//   * a softmax thread owns one query row: it pulls the 128 scores of a key tile into registers at once and hands S_g's TMEM columns straight
+//     back (s_free), so QK_g(j+1) runs under the exponentials of tile j; pv_done orders "PV_g(j) has read P_g / updated O_g" before the
+//     group rewrites P_g or rescales O_g.
 // One CTA per SM: 192 KB smem (Q 2 x 16, K ring 3 x 16, V ring 3 x 16, P 2 x 32) and 384 of the 512 TMEM columns.
 // The exp unit bounds it: 16 MUFU.EX2 / clk / SM = 2048 clk per (256 queries x 128 keys) against 1024 clk of MMAs.
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -257,7 +262,7 @@ constexpr int KV_STAGES = 3;
 constexpr int ATT2_SMEM = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 256;
 constexpr float LAZY_TAU = 8.0f;  // log2 units: rescale O only when the tile maximum exceeds the reference by more than this
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                   // [2][16 KB]
@@ -272,8 +277,9 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   uint64_t* v_empty = bars + 2 + 3 * KV_STAGES;
   uint64_t* s_full = bars + 2 + 4 * KV_STAGES;      // [2]
   uint64_t* p_full = s_full + 2;                    // [2]
-  uint64_t* o_final = p_full + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint64_t* s_free = p_full + 2;                    // [2]  softmax g holds S_g(j) in registers: QK_g(j+1) may overwrite the TMEM copy
+  uint64_t* pv_done = s_free + 2;                   // [2]  PV_g(j) complete: P_g may be rewritten, O_g may be rescaled / read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * TQ, h = blockIdx.y, b = blockIdx.z;
@@ -288,7 +294,8 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
-      mbar_init(&o_final[i], 1);
+      mbar_init(&s_free[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
@@ -308,8 +315,14 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+  pdl_wait();  // (programmatic dependent launch: the qkv rows are the predecessor's output)
+  pdl_launch();
 
-  if (warp == 8) {
+  // 384 threads = three warpgroups: two softmax groups and one of {TMA warp, MMA warp, two idle warps}.  A softmax thread keeps a whole
+  // 128-score row in registers, so the third group gives registers back (168 -> 56) and the softmax groups take them (168 -> 224).
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       const int row0 = b * p.S;
@@ -326,11 +339,18 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         tma_load_2d(sK + s * K_BYTES, &tmQK, &k_full[s], p.D + h * DH, row0 + j * TK);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], V_BYTES);
-        tma_load_2d(sV + s * V_BYTES, &tmVT, &v_full[s], j * TK, vrow);
-        tma_load_2d(sV + s * V_BYTES + V_BYTES / 2, &tmVT, &v_full[s], j * TK + 64, vrow);
+        if (p.v_direct) {
+          // 128 keys x 64 dims exactly as they lie in the qkv rows: row = key, 128 B = the head's 64 dims, 128B-swizzled -- the canonical
+          // MN-major operand layout (N = 64 contiguous, 8-key groups 1024 B apart).  Keys beyond this audio are the next audio's rows (finite;
+          // their P is 0) or beyond the tensor (TMA zero fill).
+          tma_load_2d(sV + s * V_BYTES, &tmQK, &v_full[s], 2 * p.D + h * DH, row0 + j * TK);
+        } else {
+          tma_load_2d(sV + s * V_BYTES, &tmVT, &v_full[s], j * TK, vrow);
+          tma_load_2d(sV + s * V_BYTES + V_BYTES / 2, &tmVT, &v_full[s], j * TK + 64, vrow);
+        }
       }
     }
-  } else if (warp == 9) {
+    } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);
@@ -341,12 +361,16 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + g * TK, qd + 2 * k, kd + 2 * k, idesc_s, (uint32_t)(k != 0));
       };
+      const bool v_direct = p.v_direct != 0;
+      const uint32_t idesc_pv = v_direct ? (idesc_o | (1u << 16)) : idesc_o;  // bit 16: B operand MN-major
       auto issue_pv = [&](int g, int stage, bool acc) {
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k) {
           const uint64_t pd = umma_desc_sw128(smem_u32(sP + g * P_BYTES + (k >> 2) * (P_BYTES / 2))) + 2 * (k & 3);
-          const uint64_t vd = umma_desc_sw128(smem_u32(sV + stage * V_BYTES + (k >> 2) * (V_BYTES / 2))) + 2 * (k & 3);
-          umma_bf16(tmem_base + 256 + g * DH, pd, vd, idesc_o, (uint32_t)(acc || k != 0));
+          // K-major V^T: two 64-key atoms, 32 B per 16 keys inside one; MN-major V: 16 keys = 16 rows of 128 B
+          const uint64_t vd = v_direct ? umma_desc_sw128(smem_u32(sV + stage * V_BYTES + k * 2048))
+                                       : umma_desc_sw128(smem_u32(sV + stage * V_BYTES + (k >> 2) * (V_BYTES / 2))) + 2 * (k & 3);
+          umma_bf16(tmem_base + 256 + g * DH, pd, vd, idesc_pv, (uint32_t)(acc || k != 0));
         }
       };
       mbar_wait(&k_full[0], 0);
@@ -357,29 +381,55 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         umma_commit(&s_full[g]);
       }
       umma_commit(&k_empty[0]);  // K(0) is free once both QK(0) are done
-      for (int j = 0; j < NT; ++j) {
-        const int s = j % KV_STAGES, s2 = (j + 1) % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1, ph2 = ((j + 1) / KV_STAGES) & 1;
+      // Event-driven issue: each softmax group g has at most one QK (S_g's columns handed back: s_free) and one PV (P_g published: p_full)
+      // outstanding; the issuer polls both groups and issues whatever is ready, PV first (it is what the group waits for next: pv_done
+      // guards its P buffer and O).  A fixed order (QK_A, QK_B, PV_A, PV_B) made PV_A(j) wait for group B's progress whenever the groups
+      // drift apart: 11 % of the softmax warps' time in r2j's ncu source view was that pv_done wait.
+      // QK_g(j) only needs S_g's TMEM columns back -- the group holds S_g(j-1) in registers a few hundred clocks after s_full -- so the
+      // next scores are ready long before the group has finished exponentiating.
+      int qk_j[2] = {1, 1}, pv_j[2] = {0, 0};  // next key tile per group (QK(0) was issued above)
+      int k_ready = 1, v_ready = 0;            // K / V tiles known to have landed
+      const long long t0 = clock64();
+      while (pv_j[0] < NT || pv_j[1] < NT) {
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], j & 1);  // softmax g has consumed S_g(j), (rescaled O_g,) and published P_g(j)
-          if (g == 0) mbar_wait(&v_full[s], ph);
-          tc_fence_after();
-          issue_pv(g, s, j > 0);
-          if (j + 1 == NT) umma_commit(&o_final[g]);
-          if (g == 1) umma_commit(&v_empty[s]);
-          if (j + 1 < NT) {
-            if (g == 0) {
-              mbar_wait(&k_full[s2], ph2);
-              tc_fence_after();
+          {
+            const int j = pv_j[g], s = j % KV_STAGES;
+            if (j < NT && mbar_test(&p_full[g], j & 1)) {
+              if (j >= v_ready && mbar_test(&v_full[s], (j / KV_STAGES) & 1)) v_ready = j + 1;
+              if (j < v_ready) {
+                tc_fence_after();
+                issue_pv(g, s, j > 0);
+                umma_commit(&pv_done[g]);
+                pv_j[g] = j + 1;
+                if (pv_j[g ^ 1] > j) umma_commit(&v_empty[s]);  // both groups' PV(j) are issued: V(j)'s stage is free when they complete
+              }
             }
-            issue_qk(g, s2);
-            umma_commit(&s_full[g]);
-            if (g == 1) umma_commit(&k_empty[s2]);
           }
+          {
+            const int j = qk_j[g], s = j % KV_STAGES;
+            if (j < NT && mbar_test(&s_free[g], (j - 1) & 1)) {
+              if (j >= k_ready && mbar_test(&k_full[s], (j / KV_STAGES) & 1)) k_ready = j + 1;
+              if (j < k_ready) {
+                tc_fence_after();
+                issue_qk(g, s);
+                umma_commit(&s_full[g]);
+                qk_j[g] = j + 1;
+                if (qk_j[g ^ 1] > j) umma_commit(&k_empty[s]);
+              }
+            }
+          }
+        }
+        if (clock64() - t0 > (1ll << 32)) {  // a protocol bug must trap, not hang the box (see mbar_wait)
+          printf("[bw] attn_enc2 issuer timed out: block (%d,%d,%d) qk %d %d pv %d %d\n", blockIdx.x, blockIdx.y, blockIdx.z, qk_j[0], qk_j[1], pv_j[0],
+                 pv_j[1]);
+          __trap();
         }
       }
     }
+    }  // (warps 10, 11 idle: only there so that warps 8..11 form a warpgroup for setmaxnreg)
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ---------------- softmax warpgroups: g = 0 (warps 0-3) rows [q0, q0+128), g = 1 (warps 4-7) rows [q0+128, q0+256) ----------------
     const int g = warp >> 2, wq = warp & 3;
     const int r = wq * 32 + lane;                       // row inside the tile = TMEM lane
@@ -389,39 +439,34 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
     uint8_t* sPg = sP + g * P_BYTES;
     float m_ref = -INFINITY, l = 0.f;  // m_ref in raw score units
     for (int j = 0; j < NT; ++j) {
-      mbar_wait(&s_full[g], j & 1);   // S_g(j) is complete -- and so is PV_g(j-1): MMAs execute in issue order
+      mbar_wait(&s_full[g], j & 1);   // S_g(j) is complete
       tc_fence_after();
       const int key0 = j * TK;
       const bool ragged = key0 + TK > p.S;  // only the last key tile has keys beyond S: the mask costs 2 of ~6 instructions per score
-      // Both passes keep the NEXT 32-column TMEM load in flight while the current one is processed, and fold through four independent
-      // accumulators: ncu of the first cut of this kernel showed 30 % long-scoreboard (tcgen05.ld -> wait -> use, eight times per
-      // tile) and 25 % fixed-latency stalls (32-deep dependent FMNMX / FADD chains) with only two softmax warps per scheduler.
-      float tmax = -INFINITY;
+      // The whole 128-score row of this thread goes to registers in one go and the TMEM copy is handed back at once (FlashAttention-4's
+      // one-thread-one-row softmax): maximum, exponentials and the bf16 pack then run from registers while the tensor pipe already
+      // computes S_g(j+1) into the same columns.
+      uint32_t sv[TK];
+#pragma unroll
+      for (int c = 0; c < TK / 32; ++c) tmem_ld_32x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[g]);
+      float tmax;
       {
-        uint32_t va[32], vb[32];
         float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
-        tmem_ld_32x32(tS, va);
-        tmem_ld_wait();
+        if (!ragged) {
 #pragma unroll
-        for (int c = 0; c < TK / 32; ++c) {
-          uint32_t(&cur)[32] = (c & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-          if (c + 1 < TK / 32) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
-          if (!ragged) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              t0 = fmaxf(t0, __uint_as_float(cur[i]));
-              t1 = fmaxf(t1, __uint_as_float(cur[i + 1]));
-              t2 = fmaxf(t2, __uint_as_float(cur[i + 2]));
-              t3 = fmaxf(t3, __uint_as_float(cur[i + 3]));
-            }
-          } else {
-            const int kbase = key0 + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kbase + i < p.S) t0 = fmaxf(t0, __uint_as_float(cur[i]));
+          for (int i = 0; i < TK; i += 4) {
+            t0 = fmaxf(t0, __uint_as_float(sv[i]));
+            t1 = fmaxf(t1, __uint_as_float(sv[i + 1]));
+            t2 = fmaxf(t2, __uint_as_float(sv[i + 2]));
+            t3 = fmaxf(t3, __uint_as_float(sv[i + 3]));
           }
-          if (c + 1 < TK / 32) tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < TK; ++i)
+            if (key0 + i < p.S) t0 = fmaxf(t0, __uint_as_float(sv[i]));
         }
         tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
       }
@@ -432,72 +477,53 @@ attn_enc_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         factor = (j == 0) ? 0.f : ex2_approx((m_ref - tmax) * p.scale_log2e);
         m_ref = tmax;
       }
-      if (j > 0 && __any_sync(0xffffffffu, raise)) {  // rescale this warp's 32 rows of O_g in place (PV_g(j-1) is complete)
+      if (j > 0) {
+        mbar_wait(&pv_done[g], (j - 1) & 1);  // PV_g(j-1) has read P_g and updated O_g
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, raise)) {  // rescale this warp's 32 rows of O_g in place
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tO + c * 32, v);
-          tmem_ld_wait();
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tO + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-          tmem_st_32x32(tO + c * 32, v);
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+            tmem_st_32x32(tO + c * 32, v);
+          }
+          tmem_st_wait();
+          l *= factor;
         }
-        tmem_st_wait();
-        l *= factor;
       }
       const float mb = m_ref * p.scale_log2e;
-      float lsum = 0.f;
-      {
-        uint32_t va[32], vb[32];
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-        tmem_ld_32x32(tS, va);
-        tmem_ld_wait();
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      auto exp_pack = [&](auto masked) {
 #pragma unroll
-        for (int c = 0; c < TK / 32; ++c) {
-          uint32_t(&cur)[32] = (c & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-          if (c + 1 < TK / 32) tmem_ld_32x32(tS + (c + 1) * 32, nxt);
-          float pf[32];
-          if (!ragged) {
+        for (int q = 0; q < TK / 8; ++q) {  // 8 scores -> one 16-byte chunk of the swizzled P row
+          float pf[8];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              pf[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2e, -mb));
-              pf[i + 1] = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2e, -mb));
-              pf[i + 2] = ex2_approx(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2e, -mb));
-              pf[i + 3] = ex2_approx(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2e, -mb));
-              l0 += pf[i]; l1 += pf[i + 1]; l2 += pf[i + 2]; l3 += pf[i + 3];
-            }
-          } else {
-            const int kbase = key0 + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2e, -mb));
-              pf[i] = (kbase + i < p.S) ? e : 0.f;
-              l0 += pf[i];
-            }
+          for (int i = 0; i < 8; ++i) {
+            pf[i] = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2e, -mb));
+            if (decltype(masked)::value && key0 + q * 8 + i >= p.S) pf[i] = 0.f;
           }
-          uint8_t* atom = sPg + (c >> 1) * (P_BYTES / 2) + r * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_bf16(pf[q * 8 + 0], pf[q * 8 + 1]);
-            w.y = pack_bf16(pf[q * 8 + 2], pf[q * 8 + 3]);
-            w.z = pack_bf16(pf[q * 8 + 4], pf[q * 8 + 5]);
-            w.w = pack_bf16(pf[q * 8 + 6], pf[q * 8 + 7]);
-            const int chunk = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ (r & 7)) << 4)) = w;
-          }
-          if (c + 1 < TK / 32) tmem_ld_wait();
+          l0 += pf[0] + pf[4]; l1 += pf[1] + pf[5]; l2 += pf[2] + pf[6]; l3 += pf[3] + pf[7];
+          uint4 w;
+          w.x = pack_bf16(pf[0], pf[1]);
+          w.y = pack_bf16(pf[2], pf[3]);
+          w.z = pack_bf16(pf[4], pf[5]);
+          w.w = pack_bf16(pf[6], pf[7]);
+          uint8_t* atom = sPg + (q >> 3) * (P_BYTES / 2) + r * 128;
+          *reinterpret_cast<uint4*>(atom + (((q & 7) ^ (r & 7)) << 4)) = w;
         }
-        lsum = (l0 + l1) + (l2 + l3);
-      }
-      l += lsum;
+      };
+      if (!ragged) exp_pack(std::false_type{});
+      else exp_pack(std::true_type{});
+      l += (l0 + l1) + (l2 + l3);
       fence_proxy_async_smem();  // P visible to the tensor core's async-proxy reads
-      tc_fence_before();         // our tcgen05.ld of S (and st of O) are complete before the issuer touches S / O again
+      tc_fence_before();         // our tcgen05.st of O are complete before the issuer accumulates into it
       mbar_arrive(&p_full[g]);
     }
     // ---- final O_g
-    mbar_wait(&o_final[g], 0);
+    mbar_wait(&pv_done[g], (NT - 1) & 1);
     tc_fence_after();
     const int q = q0 + g * TQ + r;
     const float inv = 1.0f / l;
@@ -610,10 +636,15 @@ int attn_enc_tc(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int
 
 int attn_enc_tc2(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, int B, int S, int Spad, int H) {
   const int D = H * DH;
-  BW_CHECK(Spad % 8 == 0 && Spad >= S, "attn_enc: Spad=%d must be >= S and a multiple of 8", Spad);
+  // vt == nullptr: no transposed copy of V, the kernel reads V tiles from the qkv rows as an MN-major operand
+  BW_CHECK(vt == nullptr || (Spad % 8 == 0 && Spad >= S), "attn_enc: Spad=%d must be >= S and a multiple of 8", Spad);
   CUtensorMap tmQK, tmVT;
   if (int rc = make_tmap_2d_bf16(&tmQK, qkv, (uint64_t)B * S, (uint64_t)3 * D, (uint64_t)3 * D * 2, TQ, DH)) return rc;
-  if (int rc = make_tmap_2d_bf16(&tmVT, vt, (uint64_t)B * H * DH, (uint64_t)Spad, (uint64_t)Spad * 2, DH, 64)) return rc;
+  if (vt) {
+    if (int rc = make_tmap_2d_bf16(&tmVT, vt, (uint64_t)B * H * DH, (uint64_t)Spad, (uint64_t)Spad * 2, DH, 64)) return rc;
+  } else {
+    tmVT = tmQK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     BW_CUDA_OK(cudaFuncSetAttribute(attn_enc_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
@@ -623,9 +654,9 @@ int attn_enc_tc2(cudaStream_t st, const bf16* qkv, const bf16* vt, bf16* out, in
   p.B = B; p.S = S; p.H = H; p.D = D;
   p.scale_log2e = 0.125f * LOG2E;
   p.out = out;
+  p.v_direct = vt == nullptr;
   dim3 grid((S + 2 * TQ - 1) / (2 * TQ), H, B);
-  attn_enc_tc2_kernel<<<grid, 320, ATT2_SMEM, st>>>(tmQK, tmVT, p);
-  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(launch_k(attn_enc_tc2_kernel, grid, dim3(384), (size_t)ATT2_SMEM, st, tmQK, tmVT, p));
   return 0;
 }
 

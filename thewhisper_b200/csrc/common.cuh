@@ -160,6 +160,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// non-blocking test (try_wait may park the thread for a while): for issuers that poll several barriers
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C-ABI), never as a
 // hung GPU box.  ~2^32 cycles is about 2 s at 1.9 GHz, far beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const SelectArgs a)
 template <typename OutT>
 __global__ void layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                                       OutT* __restrict__ y, int rows, int D) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -356,15 +358,13 @@ int launch_select(cudaStream_t st, const SelectArgs& a0) {
 
 int layernorm_bf16(cudaStream_t st, const float* x, const float* g, const float* b, bf16* y, int rows, int D) {
   BW_CHECK(D % 4 == 0, "layernorm: D=%d must be a multiple of 4", D);
-  layernorm_rows_kernel<bf16><<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, y, rows, D);
-  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(launch_k(layernorm_rows_kernel<bf16>, dim3((rows + 7) / 8), dim3(256), 0, st, x, g, b, y, rows, D));
   return 0;
 }
 
 int layernorm_f32(cudaStream_t st, const float* x, const float* g, const float* b, float* y, int rows, int D) {
   BW_CHECK(D % 4 == 0, "layernorm: D=%d must be a multiple of 4", D);
-  layernorm_rows_kernel<float><<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, y, rows, D);
-  BW_CUDA_OK(cudaGetLastError());
+  BW_CUDA_OK(launch_k(layernorm_rows_kernel<float>, dim3((rows + 7) / 8), dim3(256), 0, st, x, g, b, y, rows, D));
   return 0;
 }
 

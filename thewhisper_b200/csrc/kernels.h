@@ -47,7 +47,7 @@ int gemm_tc_split(cudaStream_t st, const GemmA& a, const bf16* W, int B, int row
 int gemm_tc_ksplit(int K, int ksplit);
 // Second-generation encoder GEMM (gemm_tc2.cu): CTA pairs (cta_group::2, 256 x BN tiles), persistent, double-buffered TMEM.
 // A [M, K] plain row-major; the epilogue address map splits the flat row r as b = r / rows_per_item, t = r % rows_per_item
-// (rows_per_item <= 0: one item).  No conv wrap, no positional table.  force_bn: 0 auto, 128, 256.
+// (rows_per_item <= 0: one item).  No conv wrap, no positional table.  force_bn: 0 auto, 128, 256 (+ 1000: generic epilogue, tests).
 bool gemm_tc2_supported(int M, int N, int K);
 int gemm_tc2(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, int K, int rows_per_item, const GemmEpi& epi, int force_bn);
 // CUDA-core sibling with identical semantics: on-device comparator for the tests and the bring-up fallback

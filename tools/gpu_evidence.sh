@@ -2,7 +2,7 @@
 # The gpurun calls of a round, as named sections of ONE script (round 1 left 14 one-off scripts behind):
 #     gpurun --timeout 2400 -- 'bash tools/gpu_evidence.sh <tag> <section> [<section> ...]'
 # Every section writes gpurun_out/<tag>_*; the summaries worth keeping are copied into profiles/ afterwards.
-#   tests        GPU parity tests (-m gpu), per-test durations
+#   tests        GPU parity tests (-m gpu), per-test durations (PYTEST_K='expr with spaces' selects tests)
 #   bench        the bench line (python bench.py), plus the --impl reference arm when REF=1
 #   launches     ncu launch list (gpu__time_duration.sum) of a short bench run
 #   ncu_mega     ncu --set full of the persistent decoder-step kernel
@@ -26,13 +26,13 @@ for sec in "$@"; do
   tests)
     # one pytest process per file: a trapped kernel poisons only its own process.  The CTA-pair GEMM goes first; if it fails the
     # rest of the call runs the encoder on the first-generation kernel (BW_GEMM2=0) so one bug does not cost the whole call
-    timeout 900 python -m pytest tests/test_ops_gpu.py -q -p no:cacheprovider -m gpu -k "pair" --tb=short > ${O}_tests_pair.log 2>&1
+    timeout 300 python -m pytest tests/test_ops_gpu.py -q -p no:cacheprovider -m gpu -k "pair" --tb=short > ${O}_tests_pair.log 2>&1
     tail -3 ${O}_tests_pair.log
     if ! grep -q " passed" ${O}_tests_pair.log || grep -q "failed\|error" ${O}_tests_pair.log; then export BW_GEMM2=0; echo "!! gemm_tc2 failed: BW_GEMM2=0 for the rest"; fi
     : > ${O}_tests.log
     for f in tests/test_ops_gpu.py tests/test_model_gpu.py tests/test_pipeline_gpu.py tests/test_large_gpu.py; do
       n=$(basename $f .py)
-      timeout 1500 python -m pytest $f -q -p no:cacheprovider -m gpu -s --durations=8 --tb=short ${PYTEST_ARGS} > ${O}_${n}_full.log 2>&1
+      timeout ${TEST_TIMEOUT:-600} python -m pytest $f -q -p no:cacheprovider -m gpu -s --durations=8 --tb=short ${PYTEST_ARGS} ${PYTEST_K:+-k "$PYTEST_K"} > ${O}_${n}_full.log 2>&1
       grep -E "^\[|passed|failed|FAILED|ERROR|Error" ${O}_${n}_full.log | tail -40 | tee -a ${O}_tests.log
     done ;;
   bench)
@@ -76,7 +76,7 @@ for sec in "$@"; do
     # CUDA-event time of one decoder step at several batch shapes (+ algorithmic GB/s), encoder and log-mel times
     for spec in ${STEP_SPECS:-"1:1:30" "64:1:30" "32:1:15" "64:5:30" "8:1:30"}; do
       IFS=: read -r a g c <<< "$spec"
-      BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 600 python tools/profile_decode.py 2>&1 | grep -E "decode step|encode|logmel|Error|error" | tee -a ${O}_steptime.log
+      BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 240 python tools/profile_decode.py 2>&1 | grep -E "decode step|encode|logmel|Error|error" | tee -a ${O}_steptime.log
     done ;;
   driver)
     # exactly what the driver runs at round end: the whole GPU suite in ONE process, then smoke()
@@ -87,7 +87,7 @@ for sec in "$@"; do
       for spec in "32:1:15" "64:1:30"; do
         IFS=: read -r a g c <<< "$spec"
         echo "BW_PDL=$v A=$a" | tee -a ${O}_pdl.log
-        BW_PDL=$v BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 600 python tools/profile_decode.py 2>&1 | grep -E "decode step|programmatic" | tee -a ${O}_pdl.log
+        BW_PDL=$v BW_A=$a BW_G=$g BW_CHUNK_S=$c BW_TIME=1 BW_STEPS=2 timeout 240 python tools/profile_decode.py 2>&1 | grep -E "decode step|programmatic" | tee -a ${O}_pdl.log
       done
     done ;;
   *) echo "unknown section $sec" ;;
