@@ -134,6 +134,31 @@ int bw_word_timestamps_gather(bw_engine* e, int32_t n, const int32_t* slot_map, 
 int bw_host_merge_overlapping(const int32_t* tokens, const int32_t* lens, int32_t n_seq, const double* ts,
                               int32_t* out_tokens, double* out_ts, int32_t* out_len);
 
+/* Token ids -> text / segment chunks / word chunks: what the reference's pipeline does after every generate()
+ * (AutomaticSpeechRecognitionPipeline.postprocess, TF/pipelines/automatic_speech_recognition.py:603-611 ->
+ * WhisperTokenizer._decode_asr + _collate_word_timestamps / _combine_tokens_into_words, TF/models/whisper/tokenization_whisper.py,
+ * with the seam merge above).  A bw_host_vocab is built once per tokenizer:
+ *   bytes / offsets[n_vocab + 1]: the bytes id i contributes to decoded text (byte-level pieces already mapped back to bytes);
+ *   kind[i]: 0 text or timestamp id, 1 special id that is not a language, 2 + k language k of language_names (n_languages NUL-terminated
+ *   UTF-8 names back to back); timestamp_begin = id of <|notimestamps|> + 1; render_begin = last special id + 1 (ids from there on are
+ *   written as "<|seconds|>" when words are split); eos / sot / startofprev ids; cleanup_spaces = the tokenizer's
+ *   clean_up_tokenization_spaces. */
+typedef struct bw_host_vocab bw_host_vocab;
+int bw_host_vocab_create(const uint8_t* bytes, const int64_t* offsets, int32_t n_vocab, const int32_t* kind, const char* language_names,
+                         int32_t n_languages, int32_t timestamp_begin, int32_t render_begin, int32_t eos_id, int32_t sot_id,
+                         int32_t startofprev_id, int32_t cleanup_spaces, bw_host_vocab** out);
+void bw_host_vocab_destroy(bw_host_vocab* v);
+/* One `_decode_asr` call over n_out windows: tokens = their ids back to back (lens[n_out]); token_ts / ts_lens = the per-token end times
+ * of word mode, back to back (NULL otherwise); strides[n_out][3] = (chunk_len, stride_left, stride_right) seconds where has_stride[i].
+ * mode: 0 text only, 1 segment timestamps (return_timestamps=True), 2 word timestamps (return_timestamps="word").  default_language:
+ * index into language_names used for word splitting while no language token has been seen, or -1.
+ * The result is a JSON document {"text": ..., "warn": bool, "chunks": [...]} ("chunks" as the original's `optional["chunks"]`, absent when the
+ * original returns {}; "warn" = the original logs its missing-end-timestamp warning) in a buffer owned by `v`, valid until the next call.
+ * Returns 0, or -4 where the original raises IndexError (message in bw_last_error). */
+int bw_host_decode_asr(bw_host_vocab* v, const int32_t* tokens, const int32_t* lens, int32_t n_out, const double* token_ts, const int32_t* ts_lens,
+                       const double* strides, const uint8_t* has_stride, int32_t mode, int32_t return_language, double time_precision,
+                       int32_t default_language, const char** json_out, int64_t* json_len);
+
 /* ---- single-op entry points (used by the parity tests; same kernels as the engine) --------------------------- */
 /* C[M,N] = epi(A[M,K] W[N,K]^T): impl 0 = tcgen05, 1 = CUDA-core comparator, 2 = tcgen05 CTA pairs (cta_group::2, persistent).  out_is_f32 selects the output type. */
 int bw_op_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, float alpha, int32_t act,

@@ -256,6 +256,30 @@ def golden_streaming():
         json.dump(out, f)
 
 
+def golden_decode_asr(ref_lcs):
+    """Inputs and outputs of `WhisperTokenizer._decode_asr` with the REAL reference seam merge installed (the state `import thestage_speechkit`
+    leaves the tokenizer module in): 240 random calls of oracle/decode_asr_cases.py, raised IndexErrors included."""
+    from oracle import decode_asr_cases as DC
+
+    tok = S.make_tokenizer()
+    rng = np.random.RandomState(20260923)
+    cases = []
+    n_raise = 0
+    while len(cases) < 240:
+        case = DC.random_case(rng, tok)
+        expect = DC.reference_result(case, tok, ref_lcs)
+        again = DC.reference_result(case, tok, hf_ref.lcs_merge)  # the restated merge must not change anything
+        assert expect == again, (case, expect, again)
+        if "raises" in expect:
+            n_raise += 1
+            if n_raise > 12:
+                continue
+        cases.append({"case": case, "expect": expect})
+    with open(os.path.join(GOLD, "decode_asr_cases.json"), "w") as f:
+        json.dump(cases, f)
+    print("decode_asr_cases.json", len(cases), "cases,", n_raise, "raising")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--large", action="store_true", help="also mint the large-v3-dims goldens (minutes)")
@@ -270,6 +294,8 @@ def main():
         golden_lcs(ref_lcs)
     if a.only in ("", "stream"):
         golden_streaming()
+    if a.only in ("", "decode_asr"):
+        golden_decode_asr(ref_lcs)
     if a.only in ("", "tiny"):
         golden_model(ASRPipeline, "tiny-test", "tiny10", chunk_s=10, audio_s=25.0, gain=8.0)
         golden_model(ASRPipeline, "small-test", "small30", chunk_s=30, audio_s=70.0, gain=8.0)

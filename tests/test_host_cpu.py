@@ -268,3 +268,79 @@ def test_beam_search_host_logic_matches_reference(monkeypatch):
     gk = {"num_beams": 5, "do_sample": False, "language": "en", "task": "transcribe", "max_new_tokens": 32}
     out = pipe(audio.copy(), chunk_length_s=meta["chunk_s"] - 1, batch_size=4, generate_kwargs=dict(gk))
     assert out["text"] == meta["pipeline"]["beam5"]["text"]
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# token ids -> text / chunks / words in the native library (csrc/host_decode.cu) against the installed tokenizer
+# ------------------------------------------------------------------------------------------------------------------------------
+def _native_result(dec, case):
+    from oracle import decode_asr_cases as DC
+
+    try:
+        text, opt = dec(DC.as_model_outputs(case), return_timestamps=case["return_timestamps"], return_language=case["return_language"],
+                        time_precision=case["time_precision"])
+    except IndexError:
+        return {"raises": "IndexError"}
+    return {"text": text, "optional": DC.jsonable(opt)}
+
+
+def test_native_decode_asr_golden():
+    """Fixtures minted with the REAL reference merge installed (oracle/make_golden.py --only decode_asr)."""
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.hostproc import AsrDecoder
+
+    cases = json.load(open(os.path.join(GOLD, "decode_asr_cases.json")))
+    dec = AsrDecoder(S.make_tokenizer())
+    assert len(cases) >= 100
+    n_words = 0
+    for i, c in enumerate(cases):
+        got = _native_result(dec, c["case"])
+        assert got == c["expect"], (i, c["case"]["return_timestamps"], got, c["expect"])
+        if c["case"]["return_timestamps"] == "word" and "optional" in got:
+            n_words += len(got["optional"].get("chunks", []))
+    assert n_words > 200  # the word path is really exercised
+
+
+def test_native_decode_asr_matches_tokenizer_on_random_cases():
+    """1 500 random calls (three modes x languages x strides x broken UTF-8 x multi-segment timestamps): text, chunks, word chunks,
+    floats and raised IndexErrors identical to `WhisperTokenizer._decode_asr` with the restated reference merge installed."""
+    from oracle import decode_asr_cases as DC
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.hostproc import AsrDecoder
+
+    tok = S.make_tokenizer()
+    dec = AsrDecoder(tok)
+    rng = np.random.RandomState(123)
+    kinds = {"ok": 0, "raises": 0}
+    for i in range(1500):
+        case = DC.random_case(rng, tok)
+        want = DC.reference_result(case, tok, hf_ref.lcs_merge)
+        got = _native_result(dec, case)
+        assert got == want, (i, case, got, want)
+        kinds["raises" if "raises" in want else "ok"] += 1
+    assert kinds["ok"] > 1200
+
+
+def test_native_decode_asr_cleanup_and_default_language():
+    """clean_up_tokenization_spaces=True and a tokenizer configured for a language written without spaces."""
+    from oracle import decode_asr_cases as DC
+    from oracle import hf_ref
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.hostproc import AsrDecoder
+
+    tok = S.make_tokenizer()
+    saved = (tok.clean_up_tokenization_spaces, getattr(tok, "language", None))
+    try:
+        for cleanup, language in ((True, None), (False, "japanese"), (True, "chinese")):
+            tok.clean_up_tokenization_spaces = cleanup
+            tok.language = language
+            dec = AsrDecoder(tok)
+            rng = np.random.RandomState(5 + int(cleanup))
+            for i in range(200):
+                case = DC.random_case(rng, tok)
+                want = DC.reference_result(case, tok, hf_ref.lcs_merge)
+                got = _native_result(dec, case)
+                assert got == want, (cleanup, language, i, case, got, want)
+    finally:
+        tok.clean_up_tokenization_spaces, tok.language = saved

@@ -63,6 +63,9 @@ SYMBOLS = {
     "bw_word_timestamps_batch": (C.c_int, [_P, _I, _P, _P, _P, C.c_double, _P, _I, _P]),
     "bw_word_timestamps_gather": (C.c_int, [_P, _I, _P, _I, _P, _P, C.c_double, _P, _I, _P]),
     "bw_host_merge_overlapping": (C.c_int, [_P, _P, _I, _P, _P, _P, _P]),
+    "bw_host_vocab_create": (C.c_int, [_P, _P, _I, _P, C.c_char_p, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "bw_host_vocab_destroy": (None, [_P]),
+    "bw_host_decode_asr": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.c_double, _I, _P, _P]),
     "bw_op_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _F, _I, _P, _P, _I, _I, _I, _P]),
     "bw_op_gemm_splitk": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
     "bw_op_gemm_dec": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),

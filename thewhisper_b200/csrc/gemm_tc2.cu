@@ -36,6 +36,7 @@ enum { EPI_GENERIC = 0, EPI_GELU = 1 /* bias, GELU -> 16 bit */, EPI_RESID = 2 /
 
 template <int BN, int NEW>
 struct Cfg2 {
+  static_assert(NEW == 8 || NEW == 16, "epilogue warps");
   static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the W tile
   static constexpr int EPI_BYTES = NEW * 4096;              // one 32 x 32 fp32 patch per epilogue warp
   // ring depth: what fits beside the epilogue patches in 227 KB (64 K-elements per stage, 512 MMA clocks at BN = 256)
@@ -170,7 +171,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_launch();
 
   // NEW / 4 epilogue warpgroups and one of {TMA warp, MMA warp, two idle warps}; the last hands registers to the epilogue
-  // (8 warps: two residual chunks in flight + the turned accumulator chunk want ~190; 16 warps: 640 threads leave 96 each, the epilogue takes 112)
+  // (8 warps: two residual chunks in flight + the turned accumulator chunk want ~190; 16 warps: 640 threads leave 96 each, the epilogue takes 104.
+  //  setmaxnreg moves registers inside the CTA's OWN allocation: what the epilogue threads gain must not exceed what the last warpgroup gives up
+  //  -- 8 warps: 256 x (216 - 168) <= 128 x (168 - 56); 16 warps: 512 x (104 - 96) <= 128 x (96 - 48).  r2n asked for 112 (8192 > 6144), counting the
+  //  SM's unallocated registers as available: setmaxnreg.inc then waits for ever, and no mbarrier timeout catches that.)
   if (warp >= NEW) {
   if (NEW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
@@ -220,7 +224,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   } else {
     if (NEW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ---------------- epilogue: NEW warps; warp w owns TMEM lanes [32 (w & 3), +32) = rows of this CTA's half tile, and the column slice w >> 2 ----------------
     // (16 warps for the GELU / plain 16-bit epilogues: with 8, one warp's pass over its 4 chunks took about as long as the MMAs of a K = 1280 tile,
     //  and with two accumulator stages the slowest of the 16 warps of a pair sets the pace: fc1 ran at 69 % tensor pipe, QKV at 85 %, r2m ncu)
@@ -403,18 +407,13 @@ int gemm_tc2(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, int K,
     else if (epi.act == 0 && !epi.residual && epi.out_bf16) mode = EPI_PLAIN;
   }
   if (force_mode >= 0) mode = force_mode;
-  // 16 epilogue warps where the epilogue is arithmetic on 16-bit outputs; the residual epilogue keeps 8 (it wants the registers)
-  static int epi16 = -1;
-  if (epi16 < 0) {
-    const char* ev = getenv("BW_GEMM2_EPI16");
-    epi16 = (ev && ev[0] == '1') ? 1 : 0;  // opt-in until measured (r2n)
-  }
-  const int nw = (epi16 && (mode == EPI_GELU || mode == EPI_PLAIN) && force_mode < 0) ? 16 : 8;
+  // (NEW = 16 epilogue warps for the GELU / plain epilogues was measured in r2o: 182.1 ms per 64 chunks against 177.3 with 8 -- the fifth
+  //  warpgroup costs a ring stage and 640 threads leave 104 registers per epilogue thread; only NEW = 8 is instantiated)
+  const int nw = 8;
 #define BW_TC2_CASE(BNV, MODEV, NEWV) \
   if (bn == BNV && mode == MODEV && nw == NEWV) return launch_tc2<BNV, MODEV, NEWV>(st, A, W, p, num_sms);
   BW_TC2_CASE(256, EPI_GENERIC, 8) BW_TC2_CASE(256, EPI_GELU, 8) BW_TC2_CASE(256, EPI_RESID, 8) BW_TC2_CASE(256, EPI_PLAIN, 8)
   BW_TC2_CASE(128, EPI_GENERIC, 8) BW_TC2_CASE(128, EPI_GELU, 8) BW_TC2_CASE(128, EPI_RESID, 8) BW_TC2_CASE(128, EPI_PLAIN, 8)
-  BW_TC2_CASE(256, EPI_GELU, 16) BW_TC2_CASE(256, EPI_PLAIN, 16) BW_TC2_CASE(128, EPI_GELU, 16) BW_TC2_CASE(128, EPI_PLAIN, 16)
 #undef BW_TC2_CASE
   BW_CHECK(false, "gemm_tc2: no kernel for bn=%d mode=%d", bn, mode);
   return 1;

@@ -78,3 +78,145 @@ def chunk_windows(n_samples: int, chunk_len: int, stride_left: int, stride_right
             yield start, start + length, (length, sl, sr), is_last
         if is_last:
             break
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# token ids -> text / segment chunks / word chunks (csrc/host_decode.cu: bw_host_decode_asr)
+# ------------------------------------------------------------------------------------------------------------------------------
+_OPEN_END_WARNING = ("Whisper did not predict an ending timestamp, which can happen if audio is cut off in the middle of a word. "
+                     "Also make sure WhisperTimeStampLogitsProcessor was used during generation.")
+
+
+def _bytes_to_unicode():
+    """The byte <-> printable-character table of byte-level BPE vocabularies (GPT-2's): bytes that are printable keep their code point,
+    the rest are mapped to 256 + n in order."""
+    keep = list(range(ord("!"), ord("~") + 1)) + list(range(ord("\xa1"), ord("\xac") + 1)) + list(range(ord("\xae"), ord("\xff") + 1))
+    table, n = {}, 0
+    for b in range(256):
+        if b in keep:
+            table[b] = chr(b)
+        else:
+            table[b] = chr(256 + n)
+            n += 1
+    return table
+
+
+class AsrDecoder:
+    """Native drop-in for `WhisperTokenizer._decode_asr(model_outputs, return_timestamps=..., return_language=..., time_precision=...)`
+    as the reference's pipeline calls it (TF/pipelines/automatic_speech_recognition.py:603-611), with the reference's seam merge
+    (REF thestage_speechkit/__init__.py:137-139).  The tokenizer is only read once, here: every id's byte string and kind (text /
+    special / language) go into a table held by the native library."""
+
+    def __init__(self, tokenizer):
+        import ctypes as C
+
+        from transformers.models.whisper.tokenization_whisper import LANGUAGES
+
+        from . import _lib
+
+        self._lib = _lib.load()
+        n = len(tokenizer)
+        toks = tokenizer.convert_ids_to_tokens(list(range(n)))
+        char_to_byte = {c: b for b, c in _bytes_to_unicode().items()}
+        pieces = []
+        for i, t in enumerate(toks):
+            t = t or ""
+            # the byte-level decoder's rule, per token: through the byte table if every character is in it, else the string's own UTF-8
+            if all(c in char_to_byte for c in t):
+                pieces.append(bytes(char_to_byte[c] for c in t))
+            else:
+                pieces.append(t.encode("utf-8"))
+        kinds = np.zeros(n, dtype=np.int32)
+        names: List[str] = []
+        for i in tokenizer.all_special_ids:
+            if not (0 <= i < n):
+                continue
+            name = LANGUAGES.get((toks[i] or "")[2:-2])
+            if name is None:
+                kinds[i] = 1
+            else:
+                if name not in names:
+                    names.append(name)
+                kinds[i] = 2 + names.index(name)
+        self._names = names
+        default = getattr(tokenizer, "language", None)
+        self._default_language = names.index(default) if default in names else -1
+        if default in ("chinese", "japanese", "thai", "lao", "myanmar", "cantonese") and default not in names:
+            names.append(default)  # (a tokenizer configured for a language whose token it does not have)
+            self._default_language = len(names) - 1
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(p) for p in pieces])
+        blob = np.frombuffer(b"".join(pieces) + b"\0", dtype=np.uint8).copy()
+        lang_blob = b"".join(s.encode("utf-8") + b"\0" for s in names) + b"\0"
+        self.timestamp_begin = tokenizer.convert_tokens_to_ids("<|notimestamps|>") + 1
+        h = C.c_void_p()
+        rc = self._lib.bw_host_vocab_create(blob.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), n, kinds.ctypes.data_as(C.c_void_p),
+                                            lang_blob, len(names), self.timestamp_begin, int(tokenizer.all_special_ids[-1]) + 1,
+                                            int(tokenizer.eos_token_id),
+                                            int(tokenizer.convert_tokens_to_ids("<|startoftranscript|>")),
+                                            int(tokenizer.convert_tokens_to_ids("<|startofprev|>")),
+                                            int(bool(getattr(tokenizer, "clean_up_tokenization_spaces", False))), C.byref(h))
+        if rc != 0:
+            raise RuntimeError((self._lib.bw_last_error() or b"bw_host_vocab_create failed").decode("utf-8", "replace"))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bw_host_vocab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, model_outputs, *, return_timestamps, return_language, time_precision):
+        import ctypes as C
+        import json
+
+        mode = 2 if return_timestamps == "word" else (1 if return_timestamps else 0)
+        toks, lens, tts, tts_lens, strides, has = [], [], [], [], [], []
+        for o in model_outputs:
+            ids = np.asarray(o["tokens"][0] if not isinstance(o["tokens"], list) else o["tokens"][0], dtype=np.int64).reshape(-1)
+            toks.append(ids.astype(np.int32))
+            lens.append(len(ids))
+            if mode == 2:
+                t = np.asarray(o["token_timestamps"][0], dtype=np.float64).reshape(-1)
+                tts.append(t)
+                tts_lens.append(len(t))
+            if "stride" in o:
+                strides.append([float(x) for x in o["stride"]])
+                has.append(1)
+            else:
+                strides.append([0.0, 0.0, 0.0])
+                has.append(0)
+        n_out = len(lens)
+        tok_a = np.concatenate(toks).astype(np.int32) if n_out and sum(lens) else np.zeros(1, dtype=np.int32)
+        lens_a = np.asarray(lens if n_out else [0], dtype=np.int32)
+        tts_a = (np.concatenate(tts) if sum(tts_lens) else np.zeros(1)).astype(np.float64) if mode == 2 else None
+        tts_lens_a = np.asarray(tts_lens if n_out else [0], dtype=np.int32) if mode == 2 else None
+        strides_a = np.asarray(strides if n_out else [[0.0, 0.0, 0.0]], dtype=np.float64)
+        has_a = np.asarray(has if n_out else [0], dtype=np.uint8)
+        out, out_len = C.c_char_p(), C.c_int64(0)
+        rc = self._lib.bw_host_decode_asr(self._h, tok_a.ctypes.data_as(C.c_void_p), lens_a.ctypes.data_as(C.c_void_p), n_out,
+                                          tts_a.ctypes.data_as(C.c_void_p) if mode == 2 else None,
+                                          tts_lens_a.ctypes.data_as(C.c_void_p) if mode == 2 else None,
+                                          strides_a.ctypes.data_as(C.c_void_p), has_a.ctypes.data_as(C.c_void_p), mode, int(bool(return_language)),
+                                          float(time_precision), self._default_language, C.byref(out), C.byref(out_len))
+        if rc == -4:
+            raise IndexError((self._lib.bw_last_error() or b"index out of range").decode("utf-8", "replace"))
+        if rc != 0:
+            raise RuntimeError((self._lib.bw_last_error() or b"bw_host_decode_asr failed").decode("utf-8", "replace"))
+        doc = json.loads(C.string_at(out, out_len.value).decode("utf-8"))
+        if doc.get("warn"):
+            import logging
+
+            logging.getLogger("transformers.models.whisper.tokenization_whisper").warning(_OPEN_END_WARNING)
+        if "chunks" not in doc:
+            return doc["text"], {}
+        chunks = doc["chunks"]
+        for c in chunks:
+            if "timestamp" in c:
+                c["timestamp"] = tuple(c["timestamp"])
+        return doc["text"], {"chunks": chunks}

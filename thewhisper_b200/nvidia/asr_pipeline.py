@@ -9,9 +9,10 @@ return_timestamps=None|True|"word", return_language=..., batch_size=..., generat
 
 Everything numeric below the call -- log-mel, encoder, decoder, logits rules, token selection, DTW -- runs in the CUDA
 engine through the C-ABI.  What stays on the host is what the reference keeps on the host too: the window schedule of
-chunked inference (TF/pipelines/automatic_speech_recognition.py:61-84,428-443), the token -> text state machine
-`WhisperTokenizer._decode_asr` (TF/models/whisper/tokenization_whisper.py:901-1150, reused from the installed
-transformers: it is string handling, not arithmetic) and the reference's own seam merge (hostproc.merge_overlapping).
+chunked inference (TF/pipelines/automatic_speech_recognition.py:61-84,428-443) and the token -> text / chunks / words state
+machine `WhisperTokenizer._decode_asr` (TF/models/whisper/tokenization_whisper.py:901-1150) with the reference's own seam merge
+-- both native since round 2 (csrc/host_decode.cu behind hostproc.AsrDecoder: 123 -> 24 ms for 64 windows x 128 tokens in word
+mode; `BW_HOST_DECODE=python` runs the installed tokenizer's instead, for comparison).
 There is no CPU fallback: constructing the pipeline without a CUDA device raises.
 """
 from __future__ import annotations
@@ -24,7 +25,7 @@ import torch
 from ..engine import ModelDims, WhisperEngine, engine_dtype
 from ..features import SAMPLE_RATE, num_valid_frames, pad_or_trim
 from ..generation import GenerationSettings, WhisperGenerator
-from ..hostproc import chunk_windows, install_merge
+from ..hostproc import AsrDecoder, chunk_windows, install_merge
 
 
 class ASRPipeline:
@@ -82,6 +83,10 @@ class ASRPipeline:
         self.engine: Optional[WhisperEngine] = None
         self._build_engine(self.batch_size)
         install_merge()
+        import os as _os
+
+        # tokens -> text in the native library; the installed tokenizer's own state machine only on request
+        self._asr_decode = None if _os.environ.get("BW_HOST_DECODE", "") == "python" else AsrDecoder(tokenizer)
 
     # ------------------------------------------------------------------------------------------------------------
     def _build_engine(self, capacity: int) -> None:
@@ -213,8 +218,8 @@ class ASRPipeline:
         time_precision = self.feature_extractor.chunk_length / self.engine.S
         results = []
         for outs in per_input:
-            text, optional = self.tokenizer._decode_asr(outs, return_timestamps=return_timestamps, return_language=return_language,
-                                                        time_precision=time_precision)
+            decode = self._asr_decode if self._asr_decode is not None else self.tokenizer._decode_asr
+            text, optional = decode(outs, return_timestamps=return_timestamps, return_language=return_language, time_precision=time_precision)
             results.append({"text": text, **optional})
         tm["decode_asr_s"] = _time.perf_counter() - t_ph
         self.last_timing = tm
