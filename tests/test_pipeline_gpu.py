@@ -43,6 +43,7 @@ def _check_text(got: str, ref: str, min_prefix=10, min_ratio=0.6):
     while n < min(len(a), len(b)) and a[n] == b[n]:
         n += 1
     ratio = difflib.SequenceMatcher(None, a, b).ratio()
+    print(f"\n[text] common prefix {n} of {len(b)} words (bound {min(min_prefix, len(b))}), difflib ratio {ratio:.3f} (bound {min_ratio})")
     assert n >= min(min_prefix, len(b)), (n, a[:12], b[:12])
     assert ratio >= min_ratio, ratio
     return n
@@ -61,6 +62,7 @@ def _check_words(got, ref):
             if a is not None:
                 assert abs(a - b) <= 0.1 + 1e-6, (g, r)
         close += all((a is None and b is None) or abs(a - b) <= 0.02 + 1e-6 for a, b in zip(g["timestamp"], r["timestamp"]))
+    print(f"\n[words] {n} common-prefix words, {close} with both times within one frame (bound {0.9 * len(ref):.0f})")
     assert close >= 0.9 * len(ref), (close, len(ref))
 
 
@@ -197,5 +199,6 @@ def test_streaming_on_engine(cuda):
             b = [w["text"] for w in wc + wu]
             same += sum(x == y for x, y in zip(a, b))
             total += max(len(a), len(b))
+    print(f"\n[scheduler vs solo streams] {same} of {total} words equal (bound {0.6 * total:.0f})")
     assert total > 0 and same >= 0.6 * total, (same, total)  # (near-tie flips between batch-3 and batch-1 kernels allowed)
     assert sched.backend_calls < sched.buffers_transcribed
