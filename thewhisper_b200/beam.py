@@ -40,17 +40,18 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
     # (the bookkeeping arrays are as long as this decode can get, not max_target_positions: every step gathers and concatenates
     # them -- at 64 audios x 5 beams that is the host's share of a step)
     Tmax = max_length
-    running_seq = np.full((A, G, Tmax), pad, dtype=np.int64)
+    running_seq = np.full((A, G, Tmax), pad, dtype=np.int32)  # (int32: these rows are gathered and concatenated every step)
     running_seq[:, :, :plen] = prompts[:, None, :]
     sequences = running_seq.copy()
     running_scores = np.zeros((A, G), dtype=np.float32)
     running_scores[:, 1:] = NEG
     beam_scores = np.full((A, G), NEG, dtype=np.float32)
     finished = np.zeros((A, G), dtype=bool)
-    running_bidx = np.full((A, G, Tmax), -1, dtype=np.int64)
+    running_bidx = np.full((A, G, Tmax), -1, dtype=np.int32)
     bidx = running_bidx.copy()
     unsat = np.ones((A, 1), dtype=bool)
     top_mask = np.arange(K) < G
+    ar = np.arange(A)[:, None]  # row gathers below: x[ar, idx] picks whole [Tmax] rows (np.take_along_axis would build an [A, K, Tmax] index grid)
     cur_len = plen
     steps = 0
     while True:
@@ -66,17 +67,17 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
         top_beam = np.take_along_axis(beam_of, key, 1)
         top_tok = np.take_along_axis(ct, key, 1)
         top_tok = np.where(top_tok >= 0, top_tok, pad)
-        top_seq = np.take_along_axis(running_seq, top_beam[:, :, None], 1).copy()  # [A, K, Tmax]
+        top_seq = running_seq[ar, top_beam]  # [A, K, Tmax] (a copy)
         top_seq[:, :, cur_len] = top_tok
-        top_bidx = np.take_along_axis(running_bidx, top_beam[:, :, None], 1).copy()
+        top_bidx = running_bidx[ar, top_beam]
         top_bidx[:, :, cur_len - plen] = top_beam + (np.arange(A) * G)[:, None]
         hits = (top_tok == opts.eos_token) | (cur_len + 1 >= max_length)
         # running beams of the next iteration
         run_lp = top_scores + hits.astype(np.float32) * NEG
         nxt = _topk_desc(run_lp, G)
-        running_seq = np.take_along_axis(top_seq, nxt[:, :, None], 1)
+        running_seq = top_seq[ar, nxt]
         running_scores = np.take_along_axis(run_lp, nxt, 1)
-        running_bidx = np.take_along_axis(top_bidx, nxt[:, :, None], 1)
+        running_bidx = top_bidx[ar, nxt]
         parents = np.take_along_axis(top_beam, nxt, 1)
         next_tok = np.take_along_axis(top_tok, nxt, 1)
         # finished beams
@@ -89,8 +90,8 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
         m_fin = np.concatenate([finished, did_finish], 1)
         m_bidx = np.concatenate([bidx, top_bidx], 1)
         sel = _topk_desc(m_scores, G)
-        sequences = np.take_along_axis(m_seq, sel[:, :, None], 1)
-        bidx = np.take_along_axis(m_bidx, sel[:, :, None], 1)
+        sequences = m_seq[ar, sel]
+        bidx = m_bidx[ar, sel]
         beam_scores = np.take_along_axis(m_scores, sel, 1)
         finished = np.take_along_axis(m_fin, sel, 1)
         cur_len += 1
@@ -105,10 +106,10 @@ def beam_search(eng, prompts: np.ndarray, A: int, G: int, opts, max_new: int, le
     gen: List[np.ndarray] = []
     eos_seen = []
     for a in range(A):
-        row = sequences[a, 0, plen:cur_len]
+        row = sequences[a, 0, plen:cur_len].astype(np.int64)
         cut = np.where(row == opts.eos_token)[0]
         eos_seen.append(len(cut) > 0)
         gen.append(row[: cut[0]] if len(cut) else row)
     if return_beam_indices:
-        return gen, steps, eos_seen, bidx[:, 0, :]
+        return gen, steps, eos_seen, bidx[:, 0, :].astype(np.int64)
     return gen, steps, eos_seen
