@@ -294,6 +294,20 @@ def main():
         return e0.elapsed_time(e1) / NEW_TOKENS
 
     step_ms = float(np.median([decode_only() for _ in range(5)]))
+
+    # ---- the tensor-bound part beside it: one encoder pass (32 layers + the 64 cross-K/V projections) of these A chunks, CUDA events
+    def encode_only():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.encode(A)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    try:
+        enc_ms = float(np.median([encode_only() for _ in range(5)]))
+    except Exception:  # informational: never at the cost of the line
+        enc_ms = None
     clocks = sampler.stop() if rank == 0 else None
     outs = step_e2e()
     n_words = [len(o["text"].split()) for o in outs]
@@ -310,8 +324,8 @@ def main():
     traffic, traffic_src = ncu_traffic_bytes() if (A == 1 and PRESET == "large-v3") else (None, None)
     achieved = bytes_step / (step_ms * 1e-3) / 1e9
     tokens = A * NEW_TOKENS * world
-    # log-mel (2) + conv stem (2) + 8 per encoder layer + final LayerNorm + cross K/V projections (2 per decoder layer)
-    n_enc_kernels = 2 + 2 + dims.enc_layers * 8 + 1 + 2 * dims.dec_layers
+    # log-mel (2) + conv stem (2) + 7 per encoder layer (2 LayerNorm, 4 GEMMs, attention) + final LayerNorm + cross K/V projections (2 per decoder layer)
+    n_enc_kernels = 2 + 2 + dims.enc_layers * 7 + 1 + 2 * dims.dec_layers
     mega = dec_kernels_per_step <= 2 * (3 + NEW_TOKENS)
     line = {
         "metric": "tokens_per_sec", "value": tokens / (ms_res / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -335,6 +349,16 @@ def main():
                      "traffic_source": traffic_src,
                      "bytes_per_step": bytes_step, "ms_per_decoder_step": step_ms},
     }
+    if enc_ms:
+        d, S_enc, ffn = dims.d_model, eng.S, dims.ffn
+        flop = A * (dims.enc_layers * (2.0 * S_enc * (4 * d * d + 2 * d * ffn) + 4.0 * S_enc * S_enc * d) + dims.dec_layers * 2 * 2.0 * S_enc * d * d)
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf = flop / (enc_ms * 1e-3) / 1e12
+        line["encoder"] = {"bound": "tensor", "kernel": "encoder pass: gemm_tc2_kernel (tcgen05 CTA pairs) + attn_enc_tc2_kernel, one CUDA graph", "chunks": A,
+                           "ms_per_pass": enc_ms, "flop_per_pass": flop, "achieved": tf, "unit": "TFLOP/s",
+                           "peak_sustained": pk.get("bf16_tflops_sustained"), "peak_burst": pk.get("bf16_tflops"),
+                           "frac_sustained": tf / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None,
+                           "note": "informational; B = 1 is the latency-bound case (profiles/r2jn_summary.md: 0.65 of sustained at 64 chunks)"}
     line["configs"] = configs
     if not args.no_cpu_baseline:
         try:

@@ -38,6 +38,8 @@ GK = {"num_beams": 1, "do_sample": False, "language": "en", "task": "transcribe"
 
 
 def _check_text(got: str, ref: str, min_prefix=10, min_ratio=0.6):
+    """Bounds = about a third of the measured agreement (profiles/r2q_pipeline.log; they were 8-10 words / 0.5-0.6 before): the checkpoints are chaotic by
+    construction (layer_gain 8), so one near-tie flip changes everything after it."""
     a, b = got.split(), ref.split()
     n = 0
     while n < min(len(a), len(b)) and a[n] == b[n]:
@@ -72,7 +74,7 @@ def test_pipeline_plain_and_segments_match_reference(cuda):
     meta, model, pipe = _pipe()
     audio = S.synth_audio(meta["audio_s"], seed=2000)
     out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, generate_kwargs=dict(GK))
-    _check_text(out["text"], meta["pipeline"]["plain"]["text"])
+    _check_text(out["text"], meta["pipeline"]["plain"]["text"], min_prefix=24, min_ratio=0.7)  # measured 72 of 88 words, 0.886
     plain = out["text"]
     out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, return_timestamps=True, generate_kwargs=dict(GK))
     ref = meta["pipeline"]["ts"]
@@ -80,7 +82,7 @@ def test_pipeline_plain_and_segments_match_reference(cuda):
     assert len(out["chunks"]) >= 1 and all(len(c["timestamp"]) == 2 for c in out["chunks"])
     # list input + smaller batches than chunks: the engine must give the same answer as with batch 4 (same kernels)
     outs = pipe([audio.copy(), audio[:80000].copy()], chunk_length_s=9, batch_size=2, generate_kwargs=dict(GK))
-    _check_text(outs[0]["text"], plain)
+    _check_text(outs[0]["text"], plain, min_prefix=30, min_ratio=0.75)  # measured 88 of 88, 1.000
     assert isinstance(outs[1]["text"], str) and len(outs[1]["text"]) > 0
 
 
@@ -104,7 +106,7 @@ def test_pipeline_beam_search_matches_reference(cuda):
     meta, model, pipe = _pipe(torch_dtype=torch.float16)
     audio = S.synth_audio(meta["audio_s"], seed=2000)
     out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, generate_kwargs=dict(GK, num_beams=5))
-    _check_text(out["text"], meta["pipeline"]["beam5"]["text"], min_prefix=8, min_ratio=0.5)
+    _check_text(out["text"], meta["pipeline"]["beam5"]["text"], min_prefix=16, min_ratio=0.7)  # measured 48 of 48, 1.000 (fp16 engine)
 
 
 def test_pipeline_unusual_chunk_length(cuda):
@@ -137,7 +139,7 @@ def test_pipeline_word_timestamps_under_beam_search(cuda):
     audio = S.synth_audio(meta["audio_s"], seed=2000)
     out = pipe(audio.copy(), chunk_length_s=9, batch_size=4, return_timestamps="word", generate_kwargs=dict(GK, num_beams=5))
     ref = meta["pipeline"]["word_beam5"]
-    _check_text(out["text"], ref["text"], min_prefix=6, min_ratio=0.5)
+    _check_text(out["text"], ref["text"], min_prefix=10, min_ratio=0.7)  # measured 24 of 24, 1.000
     got, want = json.loads(json.dumps(out["chunks"], default=float)), ref["chunks"]
     n = 0
     while n < min(len(got), len(want)) and got[n]["text"] == want[n]["text"]:
@@ -199,6 +201,6 @@ def test_streaming_on_engine(cuda):
             b = [w["text"] for w in wc + wu]
             same += sum(x == y for x, y in zip(a, b))
             total += max(len(a), len(b))
-    print(f"\n[scheduler vs solo streams] {same} of {total} words equal (bound {0.6 * total:.0f})")
-    assert total > 0 and same >= 0.6 * total, (same, total)  # (near-tie flips between batch-3 and batch-1 kernels allowed)
+    print(f"\n[scheduler vs solo streams] {same} of {total} words equal (bound {0.7 * total:.0f})")
+    assert total > 0 and same >= 0.7 * total, (same, total)  # (near-tie flips between batch-3 and batch-1 kernels allowed)
     assert sched.backend_calls < sched.buffers_transcribed
