@@ -349,16 +349,19 @@ def main():
                      "traffic_source": traffic_src,
                      "bytes_per_step": bytes_step, "ms_per_decoder_step": step_ms},
     }
-    if enc_ms:
-        d, S_enc, ffn = dims.d_model, eng.S, dims.ffn
-        flop = A * (dims.enc_layers * (2.0 * S_enc * (4 * d * d + 2 * d * ffn) + 4.0 * S_enc * S_enc * d) + dims.dec_layers * 2 * 2.0 * S_enc * d * d)
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        tf = flop / (enc_ms * 1e-3) / 1e12
-        line["encoder"] = {"bound": "tensor", "kernel": "encoder pass: gemm_tc2_kernel (tcgen05 CTA pairs) + attn_enc_tc2_kernel, one CUDA graph", "chunks": A,
-                           "ms_per_pass": enc_ms, "flop_per_pass": flop, "achieved": tf, "unit": "TFLOP/s",
-                           "peak_sustained": pk.get("bf16_tflops_sustained"), "peak_burst": pk.get("bf16_tflops"),
-                           "frac_sustained": tf / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None,
-                           "note": "informational; B = 1 is the latency-bound case (profiles/r2jn_summary.md: 0.65 of sustained at 64 chunks)"}
+    try:
+        if enc_ms:
+            d, S_enc, ffn = dims.d_model, eng.S, dims.ffn
+            flop = A * (dims.enc_layers * (2.0 * S_enc * (4 * d * d + 2 * d * ffn) + 4.0 * S_enc * S_enc * d) + dims.dec_layers * 2 * 2.0 * S_enc * d * d)
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            tf = flop / (enc_ms * 1e-3) / 1e12
+            line["encoder"] = {"bound": "tensor", "kernel": "encoder pass: gemm_tc2_kernel (tcgen05 CTA pairs) + attn_enc_tc2_kernel, one CUDA graph", "chunks": A,
+                               "ms_per_pass": enc_ms, "flop_per_pass": flop, "achieved": tf, "unit": "TFLOP/s",
+                               "peak_sustained": pk.get("bf16_tflops_sustained"), "peak_burst": pk.get("bf16_tflops"),
+                               "frac_sustained": tf / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None,
+                               "note": "informational; B = 1 is the latency-bound case (profiles/r2jn_summary.md: 0.65 of sustained at 64 chunks)"}
+    except Exception as ex:  # informational entry: never at the cost of the line
+        line["encoder"] = {"error": repr(ex)}
     line["configs"] = configs
     if not args.no_cpu_baseline:
         try:
