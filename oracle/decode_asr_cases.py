@@ -21,6 +21,40 @@ TB = S.TIMESTAMP_BEGIN
 LANGS = ["en", "zh", "ja", "es", "th", "de"]
 
 
+_TOK = {}
+
+
+def special_tokenizer():
+    """The synthetic tokenizer with its control tokens registered as SPECIAL tokens, as released Whisper checkpoints have them
+    (`all_special_ids` = <|endoftext|> ... <|notimestamps|>): with thewhisper_b200.synthetic.make_tokenizer() only <|endoftext|> is special, so
+    `_decode_asr` never takes its language branches there.  Same ids."""
+    if "special" in _TOK:
+        return _TOK["special"]
+    from tokenizers import AddedToken
+    from transformers import WhisperTokenizer
+
+    b2u = S._bytes_to_unicode()
+    vocab = {}
+    for b in range(256):
+        vocab[b2u[b]] = len(vocab)
+    i = 0
+    while len(vocab) < S.EOS:
+        vocab[f"\u0120w{i}"] = len(vocab)
+        i += 1
+    specials = ["<|startoftranscript|>"] + [f"<|{c}|>" for c in S.LANG_CODES] + ["<|translate|>", "<|transcribe|>", "<|startoflm|>", "<|startofprev|>",
+                                                                                 "<|nospeech|>", "<|notimestamps|>"]
+    tok = WhisperTokenizer(vocab=vocab, merges=[], pad_token="<|endoftext|>", extra_special_tokens=specials)
+    tok.add_tokens([AddedToken("<|%.2f|>" % (k * 0.02), special=False, normalized=False) for k in range(1501)])
+    assert len(tok) == S.VOCAB and tok.all_special_ids[-1] == S.NOTIMESTAMPS and len(tok.all_special_ids) == S.NOTIMESTAMPS - S.EOS + 1
+    assert tok.convert_tokens_to_ids(["<|startoftranscript|>", "<|en|>", "<|0.00|>"]) == [S.SOT, S.LANG_EN, S.TIMESTAMP_BEGIN]
+    _TOK["special"] = tok
+    return tok
+
+
+def tokenizer_of(kind: str):
+    return special_tokenizer() if kind == "special" else S.make_tokenizer()
+
+
 def _b(text: str) -> List[int]:
     return list(text.encode("utf-8"))
 

@@ -258,23 +258,26 @@ def golden_streaming():
 
 def golden_decode_asr(ref_lcs):
     """Inputs and outputs of `WhisperTokenizer._decode_asr` with the REAL reference seam merge installed (the state `import thestage_speechkit`
-    leaves the tokenizer module in): 240 random calls of oracle/decode_asr_cases.py, raised IndexErrors included."""
+    leaves the tokenizer module in): 2 x 240 random calls of oracle/decode_asr_cases.py, raised IndexErrors included."""
     from oracle import decode_asr_cases as DC
 
-    tok = S.make_tokenizer()
     rng = np.random.RandomState(20260923)
     cases = []
     n_raise = 0
-    while len(cases) < 240:
-        case = DC.random_case(rng, tok)
-        expect = DC.reference_result(case, tok, ref_lcs)
-        again = DC.reference_result(case, tok, hf_ref.lcs_merge)  # the restated merge must not change anything
-        assert expect == again, (case, expect, again)
-        if "raises" in expect:
-            n_raise += 1
-            if n_raise > 12:
-                continue
-        cases.append({"case": case, "expect": expect})
+    for kind in ("plain", "special"):  # only <|endoftext|> special (the synthetic tokenizer) / every control token special (released checkpoints)
+        tok = DC.tokenizer_of(kind)
+        n_kind = 0
+        while n_kind < 240:
+            case = DC.random_case(rng, tok)
+            expect = DC.reference_result(case, tok, ref_lcs)
+            again = DC.reference_result(case, tok, hf_ref.lcs_merge)  # the restated merge must not change anything
+            assert expect == again, (case, expect, again)
+            if "raises" in expect:
+                n_raise += 1
+                if n_raise > 24:
+                    continue
+            cases.append({"tokenizer": kind, "case": case, "expect": expect})
+            n_kind += 1
     with open(os.path.join(GOLD, "decode_asr_cases.json"), "w") as f:
         json.dump(cases, f)
     print("decode_asr_cases.json", len(cases), "cases,", n_raise, "raising")

@@ -289,12 +289,14 @@ def test_native_decode_asr_golden():
     from thewhisper_b200 import synthetic as S
     from thewhisper_b200.hostproc import AsrDecoder
 
+    from oracle import decode_asr_cases as DC
+
     cases = json.load(open(os.path.join(GOLD, "decode_asr_cases.json")))
-    dec = AsrDecoder(S.make_tokenizer())
-    assert len(cases) >= 100
+    decs = {k: AsrDecoder(DC.tokenizer_of(k)) for k in ("plain", "special")}
+    assert len(cases) >= 400 and {c["tokenizer"] for c in cases} == {"plain", "special"}
     n_words = 0
     for i, c in enumerate(cases):
-        got = _native_result(dec, c["case"])
+        got = _native_result(decs[c["tokenizer"]], c["case"])
         assert got == c["expect"], (i, c["case"]["return_timestamps"], got, c["expect"])
         if c["case"]["return_timestamps"] == "word" and "optional" in got:
             n_words += len(got["optional"].get("chunks", []))
@@ -302,24 +304,29 @@ def test_native_decode_asr_golden():
 
 
 def test_native_decode_asr_matches_tokenizer_on_random_cases():
-    """1 500 random calls (three modes x languages x strides x broken UTF-8 x multi-segment timestamps): text, chunks, word chunks,
+    """2 000 random calls (two tokenizer layouts x three modes x languages x strides x broken UTF-8 x multi-segment timestamps): text, chunks, word chunks,
     floats and raised IndexErrors identical to `WhisperTokenizer._decode_asr` with the restated reference merge installed."""
     from oracle import decode_asr_cases as DC
     from oracle import hf_ref
     from thewhisper_b200 import synthetic as S
     from thewhisper_b200.hostproc import AsrDecoder
 
-    tok = S.make_tokenizer()
-    dec = AsrDecoder(tok)
     rng = np.random.RandomState(123)
     kinds = {"ok": 0, "raises": 0}
-    for i in range(1500):
-        case = DC.random_case(rng, tok)
-        want = DC.reference_result(case, tok, hf_ref.lcs_merge)
-        got = _native_result(dec, case)
-        assert got == want, (i, case, got, want)
-        kinds["raises" if "raises" in want else "ok"] += 1
-    assert kinds["ok"] > 1200
+    languages = set()
+    for kind in ("plain", "special"):  # only <|endoftext|> special / every control token special, as in released checkpoints
+        tok = DC.tokenizer_of(kind)
+        dec = AsrDecoder(tok)
+        for i in range(1000):
+            case = DC.random_case(rng, tok)
+            want = DC.reference_result(case, tok, hf_ref.lcs_merge)
+            got = _native_result(dec, case)
+            assert got == want, (kind, i, case, got, want)
+            kinds["raises" if "raises" in want else "ok"] += 1
+            for c in want.get("optional", {}).get("chunks", []):
+                languages.add(c.get("language"))
+    assert kinds["ok"] > 1600
+    assert len(languages - {None}) >= 3  # the language branches are really taken
 
 
 def test_native_decode_asr_cleanup_and_default_language():
@@ -329,7 +336,7 @@ def test_native_decode_asr_cleanup_and_default_language():
     from thewhisper_b200 import synthetic as S
     from thewhisper_b200.hostproc import AsrDecoder
 
-    tok = S.make_tokenizer()
+    tok = DC.special_tokenizer()
     saved = (tok.clean_up_tokenization_spaces, getattr(tok, "language", None))
     try:
         for cleanup, language in ((True, None), (False, "japanese"), (True, "chinese")):
