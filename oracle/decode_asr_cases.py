@@ -60,7 +60,7 @@ def _b(text: str) -> List[int]:
 
 
 _SNIPPETS = [" hello", " world", ",", ".", " (", ")", " \"", "\"", "!", "?", " -", "-", " é", "é", " naïve", "中", "文", " 日本", "語", " \U0001f600", "ß", " ¿", "¡",
-             "。", "，", " “", "”", "'s", " n't", " .", " ,", "  ", " ", "\n", " <|1.23|>", "<|0.5|", " a", "b", "c", " 12", ".5", " :", ":", " [", "]", " {", "}"]
+             "。", "，", " “", "”", "'s", " n't", " .", " ,", "  ", " ", "\n", " <|1.23|>", "<|0.5|", "<|\u0661\u0662.\u0663|>", " <|\uff11.5|>x", "<|1.\u0e52|", "<|12.|>", " a", "b", "c", " 12", ".5", " :", ":", " [", "]", " {", "}"]
 
 
 def random_text_tokens(rng, n: int) -> List[int]:

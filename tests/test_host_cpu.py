@@ -351,3 +351,24 @@ def test_native_decode_asr_cleanup_and_default_language():
                 assert got == want, (cleanup, language, i, case, got, want)
     finally:
         tok.clean_up_tokenization_spaces, tok.language = saved
+
+
+def test_native_decode_asr_digit_table_matches_unicodedata():
+    """`<|\\d+\\.\\d+|>` is removed from chunk texts by the original with Python's Unicode-aware \\d: every Nd code point, and only those,
+    must be removed by the native table too (one probe per code point plane-by-plane would be 1.1 M calls; 20 000 sampled + all Nd)."""
+    import unicodedata
+
+    from thewhisper_b200 import synthetic as S
+    from thewhisper_b200.hostproc import AsrDecoder
+
+    dec = AsrDecoder(S.make_tokenizer())
+    nd = [c for c in range(0x110000) if unicodedata.category(chr(c)) == "Nd"]
+    rng = np.random.RandomState(0)
+    others = [int(c) for c in rng.randint(0x80, 0x110000, size=20000) if not (0xD800 <= c <= 0xDFFF) and unicodedata.category(chr(int(c))) != "Nd"]
+    for group, expect_removed in ((nd, True), (others, False)):
+        for k in range(0, len(group), 64):
+            part = group[k:k + 64]
+            text = "".join(f"[<|{chr(c)}.5|>]" for c in part)
+            out, _ = dec([{"tokens": np.asarray([list(text.encode("utf-8"))])}], return_timestamps=None, return_language=False, time_precision=0.02)
+            want = "[]" * len(part) if expect_removed else text
+            assert out == want, (expect_removed, [hex(c) for c in part][:4])

@@ -115,6 +115,22 @@ static void append_utf8(uint32_t c, std::string* o) {
   else { o->push_back((char)(0xF0 | (c >> 18))); o->push_back((char)(0x80 | ((c >> 12) & 0x3F))); o->push_back((char)(0x80 | ((c >> 6) & 0x3F))); o->push_back((char)(0x80 | (c & 0x3F))); }
 }
 
+static bool is_digit(uint32_t c) {  // `\d` of Python's `re` on str: Unicode category Nd (Unicode 15; a test checks the table against unicodedata)
+  if (c < 0x80) return c >= '0' && c <= '9';
+  static const uint32_t nd[][2] = {
+      {0x660, 0x669}, {0x6F0, 0x6F9}, {0x7C0, 0x7C9}, {0x966, 0x96F}, {0x9E6, 0x9EF}, {0xA66, 0xA6F}, {0xAE6, 0xAEF}, {0xB66, 0xB6F}, {0xBE6, 0xBEF},
+      {0xC66, 0xC6F}, {0xCE6, 0xCEF}, {0xD66, 0xD6F}, {0xDE6, 0xDEF}, {0xE50, 0xE59}, {0xED0, 0xED9}, {0xF20, 0xF29}, {0x1040, 0x1049}, {0x1090, 0x1099},
+      {0x17E0, 0x17E9}, {0x1810, 0x1819}, {0x1946, 0x194F}, {0x19D0, 0x19D9}, {0x1A80, 0x1A89}, {0x1A90, 0x1A99}, {0x1B50, 0x1B59}, {0x1BB0, 0x1BB9},
+      {0x1C40, 0x1C49}, {0x1C50, 0x1C59}, {0xA620, 0xA629}, {0xA8D0, 0xA8D9}, {0xA900, 0xA909}, {0xA9D0, 0xA9D9}, {0xA9F0, 0xA9F9}, {0xAA50, 0xAA59},
+      {0xABF0, 0xABF9}, {0xFF10, 0xFF19}, {0x104A0, 0x104A9}, {0x10D30, 0x10D39}, {0x11066, 0x1106F}, {0x110F0, 0x110F9}, {0x11136, 0x1113F},
+      {0x111D0, 0x111D9}, {0x112F0, 0x112F9}, {0x11450, 0x11459}, {0x114D0, 0x114D9}, {0x11650, 0x11659}, {0x116C0, 0x116C9}, {0x11730, 0x11739},
+      {0x118E0, 0x118E9}, {0x11950, 0x11959}, {0x11C50, 0x11C59}, {0x11D50, 0x11D59}, {0x11DA0, 0x11DA9}, {0x11F50, 0x11F59}, {0x16A60, 0x16A69},
+      {0x16AC0, 0x16AC9}, {0x16B50, 0x16B59}, {0x1D7CE, 0x1D7FF}, {0x1E140, 0x1E149}, {0x1E2F0, 0x1E2F9}, {0x1E4F0, 0x1E4F9}, {0x1E950, 0x1E959},
+      {0x1FBF0, 0x1FBF9}};
+  for (const auto& r : nd)
+    if (c >= r[0] && c <= r[1]) return true;
+  return false;
+}
 static bool is_space(uint32_t c) {  // str.isspace(): what str.strip() removes
   return (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20) || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) || c == 0x2028 ||
          c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
@@ -288,10 +304,10 @@ class Decoder {
     while (i < s.size()) {
       if (s[i] == '<' && i + 1 < s.size() && s[i + 1] == '|') {
         size_t j = i + 2, d0 = j;
-        while (j < s.size() && s[j] >= '0' && s[j] <= '9') ++j;
+        while (j < s.size() && is_digit(s[j])) ++j;
         if (j > d0 && j < s.size() && s[j] == '.') {
           size_t d1 = ++j;
-          while (j < s.size() && s[j] >= '0' && s[j] <= '9') ++j;
+          while (j < s.size() && is_digit(s[j])) ++j;
           if (j > d1 && j + 1 < s.size() && s[j] == '|' && s[j + 1] == '>') { i = j + 2; continue; }
         }
       }
